@@ -1,0 +1,189 @@
+/*
+ * stpde.h - C ABI of the B200-native decode + PDE-residual hot path.
+ *
+ * The reference (maxjiang93/space_time_pde) is pure Python and has no FFI layer; the
+ * drop-in boundary is its Python call surface.  Every entry point below
+ * replaces one reference function on that surface and is what a ctypes binding (see
+ * INTEGRATION.md) calls from the reference-side modules:
+ *
+ *   stpde_interp_coefficients  <- src/regular_nd_grid_interpolation.py:14-78
+ *                                 regular_nd_grid_interpolation_coefficients()
+ *   stpde_interp               <- src/regular_nd_grid_interpolation.py:81-104
+ *                                 regular_nd_grid_interpolation()
+ *   stpde_jet_forward          <- src/local_implicit_grid.py:10-61 query_local_implicit_grid()
+ *                                 + src/implicit_net.py:40-54 ImNet.forward()
+ *                                 + src/pde.py:8-9,115-143 PDELayer.__call__ / torch_diff
+ *                                 (values and every partial derivative the equation strings need,
+ *                                  in ONE pass: forward-mode jets instead of autograd.grad per dif())
+ *   stpde_residuals            <- src/pde.py:139-142 (evaluation of the lambdified equations)
+ *   stpde_jet_forward_host     <- same as stpde_jet_forward with HOST buffers (copies inside)
+ *
+ * Conventions
+ *   - plain C, no torch types; all sizes explicit; returns 0 on success or a negative
+ *     STPDE_E* code, never throws.  stpde_last_error() returns a thread-local message.
+ *   - device entry points take caller-owned DEVICE pointers, allocate nothing, and are
+ *     asynchronous on the given cudaStream_t (passed as void*).  Scratch memory is supplied by
+ *     the caller (stpde_workspace_bytes()).
+ *   - arithmetic is float32 end to end (cell indices int32); strides are in ELEMENTS.
+ *   - the kernels reproduce the reference's quirks: ind0 = floor(q/cubesize) ignores xmin
+ *     (python negative-index wrap, out-of-range -> status flag), clip ties have gradient 0.5.
+ */
+#ifndef STPDE_H_
+#define STPDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STPDE_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define STPDE_MAX_DIM 4
+#define STPDE_MAX_LAYERS 8
+#define STPDE_MAX_FIRST 4
+#define STPDE_MAX_SECOND 10
+#define STPDE_MAX_COMPONENTS 10 /* value + first + second components propagated by one launch */
+#define STPDE_MAX_OUT 8
+
+/* error codes */
+#define STPDE_OK 0
+#define STPDE_EINVAL (-1)     /* bad descriptor / argument */
+#define STPDE_ENOMEM (-2)     /* workspace too small */
+#define STPDE_ECUDA (-3)      /* CUDA runtime error (message in stpde_last_error) */
+#define STPDE_EINDEX (-4)     /* a query point addressed a cell outside the grid (reference: IndexError) */
+#define STPDE_EUNSUPPORTED (-5)
+#define STPDE_ERANGE (-6)     /* split-precision operand left the fp16 range (tensor-core path) */
+
+/* activations: reference src/nonlinearities.py:15-22 */
+enum {
+    STPDE_ACT_TANH = 0,
+    STPDE_ACT_RELU = 1,
+    STPDE_ACT_SOFTPLUS = 2, /* torch.nn.Softplus(beta=1, threshold=20) */
+    STPDE_ACT_ELU = 3,      /* alpha = 1 */
+    STPDE_ACT_SWISH = 4,    /* x * sigmoid(act_param * x), act_param = learnable beta */
+    STPDE_ACT_LEAKYRELU = 5 /* negative_slope = 0.01 */
+};
+
+/* arithmetic of the MLP contractions */
+enum {
+    STPDE_PREC_FP32 = 0,   /* FP32 FFMA (CUDA cores): reference-exact arithmetic */
+    STPDE_PREC_FP16X3 = 1, /* tcgen05 tensor cores, fp16 hi/lo split operands, 3 MMAs per product,
+                              fp32 accumulate: ~2^-22 operand precision (fp32 parity mode) */
+    STPDE_PREC_FP16 = 2    /* tcgen05, single fp16 pass (relaxed parity, BASELINE config 3) */
+};
+
+/*
+ * Problem descriptor.
+ *
+ * The decoder is the reference's skip-MLP (src/implicit_net.py:31-36) generalised to n_layers
+ * linear layers of output width widths[l]:  D = dim + channels;
+ *   layer 0        : in = D
+ *   layer 1..n-2   : in = widths[l-1] + D      (input re-concatenated AFTER the activation)
+ *   layer n-1      : in = widths[n-2]          (no activation; widths[n-1] = out_features)
+ * ImNet(dim, c, o, nf) is n_layers = 6, widths = {16nf, 8nf, 4nf, 2nf, nf, o}.
+ * Weight l is row-major [widths[l], in_l] (torch nn.Linear layout); input columns are ordered
+ * [activations(widths[l-1]), x_relative(dim), latent(channels)].
+ *
+ * Jet specification: first_dirs[] lists the coordinate columns whose first derivative is
+ * needed; second_pairs[][2] lists (i, j) column pairs whose second derivative is needed - both i
+ * and j must appear in first_dirs.  1 + n_first + n_second <= STPDE_MAX_COMPONENTS per call.
+ */
+typedef struct stpde_desc {
+    int32_t batch;                      /* b */
+    int32_t npts;                       /* p, query points per batch element */
+    int32_t dim;                        /* d, 1..4 */
+    int32_t grid_size[STPDE_MAX_DIM];   /* n_1..n_d */
+    int32_t channels;                   /* c */
+    int32_t n_layers;
+    int32_t widths[STPDE_MAX_LAYERS];
+    int32_t act_kind;
+    float act_param;
+    int32_t n_first;
+    int32_t first_dirs[STPDE_MAX_FIRST];
+    int32_t n_second;
+    int32_t second_pairs[STPDE_MAX_SECOND][2];
+    int32_t precision;
+    float xmin[STPDE_MAX_DIM];          /* float32 bounds exactly as the reference forms them */
+    float xmax[STPDE_MAX_DIM];
+    int32_t reserved[8];
+} stpde_desc_t;
+
+int stpde_version(void);
+const char *stpde_last_error(void);
+/* sizeof(stpde_desc_t) as compiled into the library (binding layout check). */
+size_t stpde_desc_size(void);
+
+/* Number of SMs / name of the device the library would run on (diagnostics; -1 if no device). */
+int stpde_device_sm_count(void);
+
+/* Scratch bytes stpde_jet_forward needs for this descriptor (0 on invalid descriptor). */
+size_t stpde_workspace_bytes(const stpde_desc_t *desc);
+
+/*
+ * corner_values [b,p,2^d,c], weights [b,p,2^d], x_relative [b,p,2^d,d]  (all contiguous f32).
+ * grid is [b, n_1..n_d, c] with element strides grid_strides[d+2]; q is [b,p,d] with q_strides[3].
+ * status: device int32[1], OR-ed with 1 if any point addressed a cell outside the grid.
+ */
+int stpde_interp_coefficients(int32_t batch, int32_t npts, int32_t dim, const int32_t *grid_size,
+                              int32_t channels, const float *grid, const int64_t *grid_strides,
+                              const float *q, const int64_t *q_strides, const float *xmin,
+                              const float *xmax, float *corner_values, float *weights,
+                              float *x_relative, int32_t *status, void *stream);
+
+/* out [b,p,c] = sum_j corner_j * weight_j */
+int stpde_interp(int32_t batch, int32_t npts, int32_t dim, const int32_t *grid_size, int32_t channels,
+                 const float *grid, const int64_t *grid_strides, const float *q,
+                 const int64_t *q_strides, const float *xmin, const float *xmax, float *out,
+                 int32_t *status, void *stream);
+
+/*
+ * Fused decode + jets.
+ *   W[l], B[l] : device pointers of layer l's weight / bias (host array of n_layers pointers)
+ *   y          : [b,p,o] values
+ *   jets       : [n_first + n_second, b, p, o] partial derivatives w.r.t. the query coordinates
+ *                (first-order planes in first_dirs order, then second-order planes); may be NULL
+ *                when n_first == n_second == 0
+ *   status     : device int32[1] (bit 0: index out of range, bit 1: fp16 range exceeded)
+ */
+int stpde_jet_forward(const stpde_desc_t *desc, const float *grid, const int64_t *grid_strides,
+                      const float *q, const int64_t *q_strides, const float *const *W,
+                      const float *const *B, float *y, float *jets, void *workspace,
+                      size_t workspace_bytes, int32_t *status, void *stream);
+
+/*
+ * Same computation with HOST buffers (grid, q, weights, y, jets all in host memory; grid and q
+ * contiguous).  Allocates device memory internally, copies in, runs, copies out, synchronises.
+ * This is the end-to-end entry point a non-torch caller would use.
+ */
+int stpde_jet_forward_host(const stpde_desc_t *desc, const float *grid, const float *q,
+                           const float *const *W, const float *const *B, float *y, float *jets);
+
+/*
+ * Residual evaluation: a postfix program per equation over the symbols
+ *   [ q_0..q_{d-1} | y_0..y_{o-1} | jets plane 0..n_jet-1 for every output ]  evaluated per point.
+ * prog is int32 words: (opcode, operand) pairs; consts are float32 literals.
+ *   opcodes: 0 PUSH_CONST c   1 PUSH_Q k   2 PUSH_Y i   3 PUSH_JET (plane*o + i)
+ *            4 ADD  5 MUL  6 NEG  7 POWI n  8 END (equation separator)
+ * residuals: [n_eq, b, p].
+ */
+int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                    const float *q, const int64_t *q_strides, const float *y, const float *jets,
+                    const int32_t *prog, int32_t prog_words, const float *consts, int32_t n_consts,
+                    int32_t n_eq, float *residuals, void *stream);
+
+/*
+ * Instrumentation (bench.py): every kernel launch is counted per slot; with profiling enabled each
+ * launch group is additionally bracketed by CUDA events on the launching stream.
+ * stpde_profile_read synchronises the device, fills elapsed milliseconds and launch counts per
+ * slot since the previous read, resets them and returns the number of slots.
+ */
+int stpde_profile_enable(int on);
+int stpde_profile_read(double *ms_by_slot, int64_t *launches_by_slot, int n_slots);
+const char *stpde_profile_slot_name(int slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STPDE_H_ */

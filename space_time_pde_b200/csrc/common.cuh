@@ -1,0 +1,88 @@
+// Shared device/host definitions for the stpde kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stpde.h"
+
+namespace stpde {
+
+constexpr int kMaxDim = STPDE_MAX_DIM;
+constexpr int kMaxComp = STPDE_MAX_COMPONENTS;
+constexpr int kMaxLayers = STPDE_MAX_LAYERS;
+constexpr int kMaxOut = STPDE_MAX_OUT;
+
+// status bits written by kernels
+constexpr int kStatusIndex = 1;  // cell index outside the grid (reference raises IndexError)
+constexpr int kStatusRange = 2;  // split-precision operand outside fp16 range
+
+// Jet components propagated through the MLP.  Component 0 is the value; components
+// 1..n_first are d/dxrel_{first_dirs[c-1]}; components 1+n_first.. are second derivatives whose
+// parents are the first-order components sec_a / sec_b.
+struct JetSpec {
+    int kc;
+    int n_first;
+    int n_second;
+    int first_dirs[STPDE_MAX_FIRST];
+    int sec_a[STPDE_MAX_SECOND];  // component index of d/dx_i
+    int sec_b[STPDE_MAX_SECOND];  // component index of d/dx_j
+};
+
+// Geometry of the latent grid and the clip / cell arithmetic, all float32 exactly as the
+// reference forms it (regular_nd_grid_interpolation.py:37-51).
+struct GridGeom {
+    int dim;
+    int size[kMaxDim];
+    int channels;
+    float lo[kMaxDim];        // xmin + eps
+    float hi[kMaxDim];        // xmax - eps
+    float cubesize[kMaxDim];  // (xmax - xmin) / (size - 1)
+    int64_t gstride[kMaxDim + 2];  // element strides of grid [b, n_1..n_d, c]
+    int64_t qstride[3];            // element strides of q [b, p, d]
+    int nvert;                     // prod(size)
+};
+
+// sigma, sigma', sigma'' with torch autograd conventions (reference src/nonlinearities.py:15-22).
+__device__ __forceinline__ void act_jet(int kind, float beta, float z, float& s0, float& s1, float& s2) {
+    switch (kind) {
+        case STPDE_ACT_TANH: {
+            float t = tanhf(z);
+            float u = 1.f - t * t;
+            s0 = t; s1 = u; s2 = -2.f * t * u;
+            break;
+        }
+        case STPDE_ACT_RELU: {
+            bool p = z > 0.f;
+            s0 = p ? z : 0.f; s1 = p ? 1.f : 0.f; s2 = 0.f;
+            break;
+        }
+        case STPDE_ACT_LEAKYRELU: {
+            bool p = z > 0.f;
+            s0 = p ? z : 0.01f * z; s1 = p ? 1.f : 0.01f; s2 = 0.f;
+            break;
+        }
+        case STPDE_ACT_SOFTPLUS: {
+            if (z > 20.f) { s0 = z; s1 = 1.f; s2 = 0.f; }
+            else {
+                float e = expf(z);
+                float s = e / (1.f + e);           // torch softplus_backward: z / (z + 1)
+                s0 = log1pf(e); s1 = s; s2 = s * (1.f - s);
+            }
+            break;
+        }
+        case STPDE_ACT_ELU: {
+            if (z <= 0.f) { float e = expf(z); s0 = e - 1.f; s1 = e; s2 = e; }
+            else { s0 = z; s1 = 1.f; s2 = 0.f; }
+            break;
+        }
+        default: {  // STPDE_ACT_SWISH
+            float bz = beta * z;
+            float s = 1.f / (1.f + expf(-bz));
+            float ds = s * (1.f - s);
+            s0 = z * s; s1 = s + bz * ds; s2 = beta * ds * (2.f + bz * (1.f - 2.f * s));
+            break;
+        }
+    }
+}
+
+}  // namespace stpde

@@ -1,0 +1,243 @@
+"""Fused decode + jets: the torch-facing wrapper around ``stpde_jet_forward`` (include/stpde.h).
+
+``fused_query`` replaces, in ONE kernel sequence per chunk of points,
+  reference src/local_implicit_grid.py:47-61  (corner gather, ImNet x 2^d, blend) and
+  reference src/pde.py:8-9                    (every ``torch.autograd.grad`` the equations trigger).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .equations import JetSpec
+
+_state = threading.local()
+_test_backend = None          # tests only: CPU stand-in for the kernel (see _torch_jets.py)
+DEFAULT_PRECISION = os.environ.get("STPDE_PRECISION", "fp32")
+
+
+def set_test_backend(fn) -> None:
+    """Install a stand-in jet provider (tests of the host logic on machines without a GPU)."""
+    global _test_backend
+    _test_backend = fn
+
+
+def set_default_precision(name: str) -> None:
+    global DEFAULT_PRECISION
+    if name not in _lib.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+    DEFAULT_PRECISION = name
+
+
+# ----------------------------------------------------------------------------------------------
+# jet request context: PDELayer announces which partials it needs before calling forward_method
+# ----------------------------------------------------------------------------------------------
+class JetRequest:
+    def __init__(self, spec: JetSpec):
+        self.spec = spec
+        self.records: List[Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]] = []
+
+    def __enter__(self):
+        stack = getattr(_state, "stack", None)
+        if stack is None:
+            stack = _state.stack = []
+        stack.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        _state.stack.pop()
+        return False
+
+    def lookup(self, y: torch.Tensor):
+        for rec in self.records:
+            if rec[0] is y:
+                return rec
+        return None
+
+
+def active_request() -> Optional[JetRequest]:
+    stack = getattr(_state, "stack", None)
+    return stack[-1] if stack else None
+
+
+# ----------------------------------------------------------------------------------------------
+# workspace cache (one growing byte buffer per device; the C ABI never allocates)
+# ----------------------------------------------------------------------------------------------
+_workspaces: Dict[torch.device, torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces.pop(device, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def bounds_tensors(xmin, xmax, dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """xmin / xmax conversion of reference rgi.py:39-45 (python scalar -> float32 ones * value, ...)."""
+    import numpy as np
+
+    if isinstance(xmin, (int, float)) or isinstance(xmax, (int, float)):
+        lo = float(xmin) * torch.ones([dim], dtype=torch.float32)
+        hi = float(xmax) * torch.ones([dim], dtype=torch.float32)
+    elif isinstance(xmin, (list, tuple, np.ndarray)) or isinstance(xmax, (list, tuple, np.ndarray)):
+        lo, hi = torch.as_tensor(np.asarray(xmin)), torch.as_tensor(np.asarray(xmax))
+    else:
+        lo, hi = xmin, xmax
+    lo = lo.detach().to("cpu", torch.float32).reshape(-1)
+    hi = hi.detach().to("cpu", torch.float32).reshape(-1)
+    if lo.numel() != dim or hi.numel() != dim:
+        raise ValueError(f"xmin/xmax must have {dim} entries")
+    return lo, hi
+
+
+def make_desc(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, widths: Sequence[int],
+              act: str, act_param: float, spec: JetSpec, precision: str) -> _lib.StpdeDesc:
+    d = _lib.StpdeDesc()
+    dim = q.shape[-1]
+    d.batch, d.npts, d.dim = int(q.shape[0]), int(q.shape[1]), dim
+    for k in range(dim):
+        d.grid_size[k] = int(grid.shape[1 + k])
+        d.xmin[k] = float(lo[k])
+        d.xmax[k] = float(hi[k])
+    d.channels = int(grid.shape[-1])
+    d.n_layers = len(widths)
+    for l, w in enumerate(widths):
+        d.widths[l] = int(w)
+    d.act_kind = _lib.ACT_CODES[act]
+    d.act_param = float(act_param)
+    d.n_first = len(spec.first)
+    for i, k in enumerate(spec.first):
+        d.first_dirs[i] = k
+    d.n_second = len(spec.second)
+    for i, (a, b) in enumerate(spec.second):
+        d.second_pairs[i][0] = a
+        d.second_pairs[i][1] = b
+    d.precision = _lib.PRECISIONS[precision]
+    return d
+
+
+def _i64(values) -> ctypes.Array:
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+
+
+def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
+                Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
+                spec: JetSpec, precision: str, check: bool = True):
+    """One C-ABI call per <=10-component sub-spec; returns y [b,p,o], jets [n_jet,b,p,o] or None."""
+    if _test_backend is not None and not q.is_cuda:
+        return _test_backend(grid, q, lo, hi, Ws, bs, act, act_param, spec)
+    if not (grid.is_cuda and q.is_cuda):
+        raise RuntimeError("the fused decode path needs CUDA tensors (there is no CPU fallback); "
+                           f"got grid on {grid.device}, query_pts on {q.device}")
+    lib = _lib.load()
+    device = q.device
+    if grid.dtype != torch.float32 or q.dtype != torch.float32:
+        raise TypeError("the fused decode path is float32 (reference arithmetic); got "
+                        f"{grid.dtype} / {q.dtype}")
+    Wc = [w.detach().to(device=device, dtype=torch.float32).contiguous() for w in Ws]
+    Bc = [v.detach().to(device=device, dtype=torch.float32).contiguous() for v in bs]
+    widths = [w.shape[0] for w in Wc]
+    b, p, dim = q.shape
+    o = widths[-1]
+    y = torch.empty(b, p, o, dtype=torch.float32, device=device)
+    jets = torch.empty(spec.n_jet, b, p, o, dtype=torch.float32, device=device) if spec.n_jet else None
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    wptr = (ctypes.c_void_p * len(Wc))(*[w.data_ptr() for w in Wc])
+    bptr = (ctypes.c_void_p * len(Bc))(*[v.data_ptr() for v in Bc])
+    gstr, qstr = _i64(grid.stride()), _i64(q.stride())
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for sub in spec.split(_lib.MAX_COMPONENTS):
+            desc = make_desc(grid, q, lo, hi, widths, act, act_param, sub, precision)
+            nbytes = lib.stpde_workspace_bytes(ctypes.byref(desc))
+            if nbytes == 0:
+                raise _lib.StpdeError(-1, lib.stpde_last_error().decode())
+            ws = _workspace(device, nbytes)
+            if sub is spec:
+                sub_jets = jets
+            else:
+                sub_jets = torch.empty(sub.n_jet, b, p, o, dtype=torch.float32, device=device)
+            rc = lib.stpde_jet_forward(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr, bptr,
+                                       y.data_ptr(), sub_jets.data_ptr() if sub_jets is not None else None,
+                                       ws.data_ptr(), ws.numel(), status.data_ptr(), stream)
+            _lib.check(rc)
+            if sub is not spec:
+                nf = len(spec.first)
+                jets[:nf] = sub_jets[:nf]
+                for i, pair in enumerate(sub.second):
+                    jets[nf + spec.second.index(pair)] = sub_jets[nf + i]
+    if check and os.environ.get("STPDE_ASYNC", "0") != "1":
+        flags = int(status.item())
+        if flags & 1:
+            raise IndexError("query point addressed a cell outside the latent grid "
+                             "(reference regular_nd_grid_interpolation.py:52 ignores xmin; use xmin = 0)")
+        if flags & 2:
+            raise _lib.StpdeError(-6, "activation left the fp16 range of the split-precision tensor-core path; "
+                                      "use precision='fp32'")
+    return y, jets
+
+
+class FusedJetQuery(torch.autograd.Function):
+    """(grid, q, *params) -> (y, jets).  Backward re-evaluates the jets with torch ops (see _torch_jets.py)."""
+
+    @staticmethod
+    def forward(ctx, grid, q, lo, hi, act, act_param_t, spec, precision, n_layers, *params):
+        Ws, bs = params[:n_layers], params[n_layers:]
+        beta = float(act_param_t.detach()) if act_param_t is not None else 1.0
+        y, jets = raw_forward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision)
+        ctx.save_for_backward(grid, q, act_param_t if act_param_t is not None else torch.empty(0), *params)
+        ctx.meta = (lo, hi, act, spec, n_layers, act_param_t is not None)
+        if jets is None:
+            jets = y.new_empty(0)
+            ctx.mark_non_differentiable(jets)
+        return y, jets
+
+    @staticmethod
+    def backward(ctx, gy, gjets):
+        from ._torch_jets import query_jets
+
+        grid, q, beta_t, *params = ctx.saved_tensors
+        lo, hi, act, spec, n_layers, has_beta = ctx.meta
+        needs = ctx.needs_input_grad
+        with torch.enable_grad():
+            grid_ = grid.detach().requires_grad_(needs[0])
+            q_ = q.detach().requires_grad_(needs[1])
+            beta_ = beta_t.detach().requires_grad_(needs[5]) if has_beta else None
+            params_ = [t.detach().requires_grad_(needs[9 + i]) for i, t in enumerate(params)]
+            y, jets = query_jets(grid_, q_, lo.to(q.device), hi.to(q.device), params_[:n_layers], params_[n_layers:],
+                                 act, beta_, spec)
+            outs, gouts = [y], [gy]
+            if jets is not None and gjets is not None and gjets.numel():
+                outs.append(jets)
+                gouts.append(gjets)
+            wanted = [(0, grid_)] * needs[0] + [(1, q_)] * needs[1] + ([(5, beta_)] if has_beta and needs[5] else [])
+            wanted += [(9 + i, t) for i, t in enumerate(params_) if needs[9 + i]]
+            grads = torch.autograd.grad(outs, [t for _, t in wanted], gouts, allow_unused=True) if wanted else []
+        result = [None] * (9 + len(params))
+        for (slot, _), g in zip(wanted, grads):
+            result[slot] = g
+        return tuple(result)
+
+
+def fused_query(grid: torch.Tensor, q: torch.Tensor, xmin, xmax, layers, act: str, act_param,
+                spec: Optional[JetSpec] = None, precision: Optional[str] = None):
+    """y [b,p,o] (and jets [n_jet,b,p,o] when ``spec`` asks for derivatives)."""
+    spec = spec or JetSpec()
+    precision = precision or DEFAULT_PRECISION
+    lo, hi = bounds_tensors(xmin, xmax, q.shape[-1], q.device)
+    Ws = [l.weight for l in layers]
+    bs = [l.bias for l in layers]
+    y, jets = FusedJetQuery.apply(grid, q, lo, hi, act, act_param, spec, precision, len(layers), *Ws, *bs)
+    return y, (jets if spec.n_jet else None)

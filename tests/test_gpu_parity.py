@@ -1,0 +1,314 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  (1) golden vectors of the real reference (fp64 runs; gate = max(1e-5, reference's own fp32 noise)),
+  (2) the numpy fp64 oracle on seeded inputs,
+  (3) size-independent properties at BASELINE.json's full size (2^20 points, ImNet nf=128).
+Tolerance: rel-L-infinity 1e-5 (BASELINE.json north_star), written next to every assert."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import space_time_pde_b200 as sp
+from oracle import jet_oracle as jo
+from space_time_pde_b200 import _lib, jets
+from space_time_pde_b200.equations import JetSpec
+from tests.helpers import RB2_CASES, custom_equations, load_case, rel_linf
+from tests.test_host_logic import bounds, build_model
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+PRECISIONS = [p for p in os.environ.get("STPDE_TEST_PRECISIONS", "fp32").split(",") if p]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need CUDA (the hot path has no CPU fallback)"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(params=PRECISIONS)
+def precision(request):
+    jets.set_default_precision(request.param)
+    yield request.param
+    jets.set_default_precision("fp32")
+
+
+def full_hessian_spec(d):
+    return JetSpec(tuple(range(d)), tuple((a, b) for a in range(d) for b in range(a, d)))
+
+
+def to_dev(x, dev):
+    return x.to(dev) if torch.is_tensor(x) else x
+
+
+# ---------------------------------------------------------------------------------------------
+# interpolation kernels (reference regular_nd_grid_interpolation_test.py:12-40 + golden tensors)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_identity_grid_known_answer(d, dev):
+    axes = torch.meshgrid(*([torch.arange(11)] * d), indexing="ij")
+    grid = torch.stack(axes, dim=-1).unsqueeze(0).float().to(dev)
+    torch.manual_seed(d)
+    pts = torch.rand(1, 100, d, device=dev)
+    out = sp.regular_nd_grid_interpolation(grid, pts, 0., 1.)
+    np.testing.assert_allclose(out.cpu().numpy(), (pts * 10.).cpu().numpy(), atol=1e-4)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_interp_coefficients_bitwise_vs_reference(d, dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "interp_identity.npz"))
+    grid, pts = torch.tensor(z[f"grid{d}"]).to(dev), torch.tensor(z[f"pts{d}"]).to(dev)
+    cv, w, xr = sp.regular_nd_grid_interpolation_coefficients(grid, pts, 0., 1.)
+    np.testing.assert_array_equal(cv.cpu().numpy(), z[f"cv{d}"])
+    np.testing.assert_array_equal(w.cpu().numpy(), z[f"w{d}"])        # same IEEE fp32 operations, same order
+    np.testing.assert_array_equal(xr.cpu().numpy(), z[f"xr{d}"])
+    out = sp.regular_nd_grid_interpolation(grid, pts, 0., 1.)
+    np.testing.assert_allclose(out.cpu().numpy(), z[f"out{d}"], atol=1e-6)
+
+
+def test_interp_noncontiguous_grid_and_index_error(dev):
+    torch.manual_seed(0)
+    base = torch.randn(2, 8, 3, 5, 4, device=dev)              # [b, c, n1, n2, n3]
+    grid = base.permute(0, 2, 3, 4, 1)                          # channels-last view (quirk Q6)
+    pts = torch.rand(2, 64, 3, device=dev)
+    a = sp.regular_nd_grid_interpolation(grid, pts, 0., 1.)
+    b = sp.regular_nd_grid_interpolation(grid.contiguous(), pts, 0., 1.)
+    assert torch.equal(a, b)
+    ref = jo.interp(grid.cpu().numpy(), pts.cpu().numpy(), 0., 1., dtype=np.float32)
+    np.testing.assert_allclose(a.cpu().numpy(), ref, atol=1e-6)
+    with pytest.raises(IndexError):                              # quirk Q1: xmin > 0 walks off the grid
+        sp.regular_nd_grid_interpolation(grid, pts + 2.0, 2.0, 3.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the real reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(RB2_CASES))
+def test_rb2_golden(name, dev, precision):
+    c = load_case(name)
+    model = build_model(c, 4).to(dev)
+    layer = sp.get_rb2_pde_layer(**RB2_CASES[name])
+    grid, q = torch.tensor(c["grid"]).to(dev), torch.tensor(c["q"]).to(dev)
+    xmin, xmax = (to_dev(t, dev) for t in bounds(c))
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, xmin, xmax))
+    with torch.no_grad():
+        y, res = layer(q)
+    assert rel_linf(y.cpu().numpy(), c["y_f64"]) < TOL
+    for k, v in res.items():
+        gate = max(TOL, 2 * rel_linf(c[f"res_{k}_f32"], c[f"res_{k}_f64"]))
+        assert rel_linf(v.cpu().numpy(), c[f"res_{k}_f64"]) < gate, k
+
+
+@pytest.mark.parametrize("name,o", [("rb2_tanh", 4), ("rb2_softplus", 4), ("rb2_elu", 4), ("rb2_swish", 4),
+                                    ("rb2_relu", 4), ("rb2_leakyrelu", 4), ("rb2_ties_softplus", 4),
+                                    ("rb2_nonunit_tanh", 4), ("diffusion_leakyrelu", 2), ("ns3d_swish", 4),
+                                    ("generic_d1_softplus", 2), ("generic_d2_softplus", 3),
+                                    ("generic_d4_softplus", 3)])
+def test_all_partials_golden(name, o, dev, precision):
+    """Every first and second partial (full Hessian; d=4 needs 15 components -> two launches)."""
+    c = load_case(name)
+    model = build_model(c, o).to(dev)
+    d = int(c["dim"])
+    spec = full_hessian_spec(d)
+    grid, q = torch.tensor(c["grid"]).to(dev), torch.tensor(c["q"]).to(dev)
+    xmin, xmax = bounds(c)
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q, xmin, xmax, list(model.fc), c["act"],
+                               model.activ.beta if c["act"] == "swish" else None, spec=spec)
+    assert rel_linf(y.cpu().numpy(), c["y_f64"]) < TOL
+    jt = jt.cpu().numpy()
+    for a in range(d):
+        ref = c["g1_f64"][..., a]
+        assert rel_linf(jt[spec.plane((a,))], ref) < max(TOL, 2 * rel_linf(c["g1_f32"][..., a], ref)), f"d{a}"
+        for b in range(a, d):
+            ref = c["g2_f64"][..., a, b]
+            if np.max(np.abs(ref)) == 0:
+                assert np.max(np.abs(jt[spec.plane((a, b))])) == 0
+                continue
+            gate = max(TOL, 2 * rel_linf(c["g2_f32"][..., a, b], ref))
+            assert rel_linf(jt[spec.plane((a, b))], ref) < gate, f"d{a}d{b}"
+
+
+@pytest.mark.parametrize("name,o", [("diffusion_leakyrelu", 2), ("ns3d_swish", 4), ("generic_d1_softplus", 2),
+                                    ("generic_d2_softplus", 3), ("generic_d4_softplus", 3)])
+def test_custom_equations_golden(name, o, dev, precision):
+    c = load_case(name)
+    model = build_model(c, o).to(dev)
+    in_vars, out_vars, eqs = custom_equations(name, int(c["dim"]), o)
+    layer = sp.PDELayer(", ".join(in_vars), ", ".join(out_vars))
+    for k, (s, _) in eqs.items():
+        layer.add_equation(s, k)
+    grid, q = torch.tensor(c["grid"]).to(dev), torch.tensor(c["q"]).to(dev)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    with torch.no_grad():
+        y, res = layer(q)
+    assert rel_linf(y.cpu().numpy(), c["y_f64"]) < TOL
+    for k, v in res.items():
+        gate = max(TOL, 2 * rel_linf(c[f"res_{k}_f32"], c[f"res_{k}_f64"]))
+        assert rel_linf(v.cpu().numpy(), c[f"res_{k}_f64"]) < gate, k
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle on seeded inputs: realistic shapes, every activation, strided inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["tanh", "relu", "softplus", "elu", "swish", "leakyrelu"])
+def test_oracle_parity_paper_shape(act, dev, precision):
+    """latent 4x16x16x32 (UNet3d output shape), nf=16, 1024 points, RB2 + continuity."""
+    torch.manual_seed(hash(act) % 1000)
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=16, activation=sp.NONLINEARITIES[act]).to(dev)
+    base = torch.randn(2, 32, 4, 16, 16, device=dev) * 0.5
+    grid = base.permute(0, 2, 3, 4, 1)                           # non-contiguous view, train.py:60
+    q1 = torch.rand(1, 1024, 3, device=dev)
+    q = q1.expand(2, -1, -1)                                     # stride-0 batch, train.py:153
+    kw = dict(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer = sp.get_rb2_pde_layer(**kw)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    with torch.no_grad():
+        y, res = layer(q)
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    beta = float(model.activ.beta) if act == "swish" else 1.0
+    qn = q.cpu().numpy()
+    yj = jo.query_jet(grid.cpu().numpy(), qn, 0., 1., Ws, bs, act, beta)
+    iv, ov, eqs = jo.rb2_equations(**kw)
+    ref = jo.pde_residuals(yj, qn, iv, ov, eqs)
+    assert rel_linf(y.cpu().numpy(), yj.v) < TOL                 # 1e-5 rel-Linf vs fp64 oracle
+    for k, v in res.items():
+        assert rel_linf(v.cpu().numpy(), ref[k]) < TOL, k
+
+
+def test_host_buffer_entry_point(dev):
+    """stpde_jet_forward_host: plain C call with numpy buffers (what a non-torch binding would use)."""
+    c = load_case("rb2_softplus")
+    lib = _lib.load()
+    grid = np.ascontiguousarray(c["grid"], dtype=np.float32)
+    q = np.ascontiguousarray(c["q"], dtype=np.float32)
+    spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
+    lo, hi = jets.bounds_tensors(0., 1., 3, "cpu")
+    desc = jets.make_desc(torch.tensor(grid), torch.tensor(q), lo, hi, [W.shape[0] for W in c["Ws"]], "softplus", 1.0,
+                          spec, "fp32")
+    Ws = [np.ascontiguousarray(W, dtype=np.float32) for W in c["Ws"]]
+    bs = [np.ascontiguousarray(b, dtype=np.float32) for b in c["bs"]]
+    wp = (ctypes.c_void_p * 6)(*[W.ctypes.data for W in Ws])
+    bp = (ctypes.c_void_p * 6)(*[b.ctypes.data for b in bs])
+    y = np.empty(q.shape[:2] + (4,), dtype=np.float32)
+    jt = np.empty((5,) + y.shape, dtype=np.float32)
+    rc = lib.stpde_jet_forward_host(ctypes.byref(desc), grid.ctypes.data, q.ctypes.data, wp, bp, y.ctypes.data,
+                                    jt.ctypes.data)
+    assert rc == 0, lib.stpde_last_error()
+    assert rel_linf(y, c["y_f64"]) < TOL
+    for i, a in enumerate((0, 1, 2)):
+        assert rel_linf(jt[i], c["g1_f64"][..., a]) < TOL
+    assert rel_linf(jt[3], c["g2_f64"][..., 1, 1]) < max(TOL, 2 * rel_linf(c["g2_f32"][..., 1, 1], c["g2_f64"][..., 1, 1]))
+
+
+def test_residual_kernel_matches_torch_route(dev):
+    c = load_case("rb2_paper_softplus")
+    model = build_model(c, 4).to(dev)
+    layer = sp.get_rb2_pde_layer(**RB2_CASES["rb2_paper_softplus"])
+    grid, q = torch.tensor(c["grid"]).to(dev), torch.tensor(c["q"]).to(dev)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    with torch.no_grad():
+        _, res_kernel = layer(q)
+    grid.requires_grad_(True)                                   # forces the differentiable torch route
+    _, res_torch = layer(q)
+    for k in res_kernel:
+        assert rel_linf(res_kernel[k].cpu().numpy(), res_torch[k].detach().cpu().numpy()) < 1e-6
+
+
+def test_training_step_gradients(dev):
+    """loss.backward() through the fused Function vs the reference algorithm's autograd (CPU port)."""
+    from oracle import ref_port as rp
+
+    c = load_case("rb2_tanh")
+    model = build_model(c, 4).to(dev)
+    grid = torch.tensor(c["grid"]).to(dev).requires_grad_(True)
+    q = torch.tensor(c["q"]).to(dev)
+    kw = RB2_CASES["rb2_tanh"]
+    layer = sp.get_rb2_pde_layer(**kw)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    y, res = layer(q)
+    loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+    loss.backward()
+    port = rp.SkipMLP(c["Ws"], c["bs"], "tanh")
+    grid2 = torch.tensor(c["grid"], requires_grad=True)
+    iv, ov, eqs = jo.rb2_equations(**kw)
+    y2, res2 = rp.values_and_residuals(port, grid2, torch.tensor(c["q"]), 0., 1., iv, ov, rp.compile_equations(eqs))
+    loss2 = y2.abs().mean() + 0.0125 * torch.stack(list(res2.values())).abs().mean()
+    loss2.backward()
+    assert abs(loss.item() - loss2.item()) < 1e-5 * abs(loss2.item())
+    assert rel_linf(grid.grad.cpu().numpy(), grid2.grad.numpy()) < 1e-4
+    for i in range(6):
+        assert rel_linf(model.fc[i].weight.grad.cpu().numpy(), port.layers[i].weight.grad.numpy()) < 1e-4, i
+
+
+def test_reference_shape_tests(dev):
+    """reference local_implicit_grid_test.py:16-30 (d=3 and d=4) and the integration test shapes."""
+    for n_dim in (3, 4):
+        q = torch.rand(8, 512, n_dim, device=dev)
+        model = sp.ImNet(dim=n_dim, in_features=32, out_features=3, nf=16).to(dev)
+        grid = torch.rand(8, *([16] * n_dim), 32, device=dev)
+        with torch.no_grad():
+            out = sp.query_local_implicit_grid(model, grid, q, 0., 1.)
+        assert tuple(out.shape) == (8, 512, 3)
+        assert torch.isfinite(out).all()
+    layer = sp.PDELayer('t, x, z', 'p, b, u, w')
+    layer.add_equation('u*dif(b,x)', 'transport_eqn_b')
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=16).to(dev)
+    grid = torch.rand(8, 16, 16, 16, 32, device=dev)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    val, res = layer(torch.rand(8, 1024, 3, device=dev))
+    assert tuple(val.shape) == (8, 1024, 4) and tuple(res['transport_eqn_b'].shape) == (8, 1024, 1)
+
+
+def test_generic_decoder_module(dev):
+    """Any nn.Module mapping [N, d+c] -> [N, o] is accepted (reference docstring, lig.py:31-32)."""
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(3 + 6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2)).to(dev)
+    grid = torch.randn(2, 4, 5, 3, 6, device=dev)
+    q = torch.rand(2, 50, 3, device=dev)
+    with torch.no_grad():
+        out = sp.query_local_implicit_grid(net, grid, q, 0., 1.)
+    cv, w, xr = jo.interp_coefficients(grid.cpu().numpy(), q.cpu().numpy(), 0., 1., dtype=np.float32)
+    rows = torch.tensor(np.concatenate([xr, cv], axis=-1)).to(dev)
+    ref = (net(rows.reshape(-1, 9)).reshape(2, 50, 8, 2) * torch.tensor(w).to(dev).unsqueeze(-1)).sum(-2)
+    assert rel_linf(out.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json config 2: 2^20 points, latent 4x16x16x32, ImNet nf=128)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(dev, precision):
+    torch.manual_seed(0)
+    n = 1 << 20
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=128, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 4, 16, 16, 32, device=dev) * 0.5
+    q = torch.rand(1, n, 3, device=dev) * (1 - 2e-6) + 1e-6
+    spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), "softplus", None, spec=spec)
+        # (1) chunk / batch independence: any subset evaluated alone gives the same numbers
+        idx = torch.randperm(n, device=dev)[:4096]
+        ys, js = sp.fused_query(grid, q[:, idx], 0., 1., list(model.fc), "softplus", None, spec=spec)
+        assert torch.equal(ys, y[:, idx]) and torch.equal(js, jt[:, :, idx])
+        # (2) partition of unity: a decoder whose last layer is constant blends to that constant
+        model.fc[5].weight.zero_()
+        model.fc[5].bias.copy_(torch.tensor([1.0, -2.0, 0.5, 3.0], device=dev))
+        yc, jc = sp.fused_query(grid, q[:, :65536], 0., 1., list(model.fc), "softplus", None, spec=spec)
+        assert (yc - model.fc[5].bias).abs().max() < 2e-6
+        assert jc.abs().max() < 1e-3          # sum_j dw_j = 0 up to fp32 rounding of 1/cubesize-scaled terms
+    # (3) spot check against the fp64 oracle on a slice
+    torch.manual_seed(1)
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=128, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q[:, :256], 0., 1., list(model.fc), "softplus", None, spec=spec)
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    yj = jo.query_jet(grid.cpu().numpy(), q[:, :256].cpu().numpy(), 0., 1., Ws, bs, "softplus")
+    assert rel_linf(y.cpu().numpy(), yj.v) < TOL
+    jt = jt.cpu().numpy()
+    for i, a in enumerate((0, 1, 2)):
+        assert rel_linf(jt[i], yj.g[a]) < TOL
+    assert rel_linf(jt[3], yj.h[1][1]) < TOL and rel_linf(jt[4], yj.h[2][2]) < TOL
