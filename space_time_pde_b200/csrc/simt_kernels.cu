@@ -592,7 +592,11 @@ __global__ void residual_kernel(ResidualProgram prog, int npts, int64_t total_pt
 // ----------------------------------------------------------------------------------------------
 // host-side launchers
 // ----------------------------------------------------------------------------------------------
-static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block > 148 * 32 ? 148 * 32 : (n + block - 1) / block); }
+static inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g > 148 * 32) g = 148 * 32;  // grid-stride loops: a few waves of the 148 SMs
+    return (int)(g < 1 ? 1 : g);
+}
 
 void launch_interp_coeff(const GridGeom& g, int batch, int npts, const float* grid, const float* q,
                          float* cv, float* w, float* xr, int* status, cudaStream_t st) {
@@ -622,6 +626,7 @@ void launch_vertex_bias(const GridGeom& g, int nvert_total, const NetDesc& net, 
 void launch_pack_weights(const float* W, int N, int in_features, int kh, int dim, int Np, int Kp, float* Wh,
                          float* Wx, cudaStream_t st) {
     int64_t total = (int64_t)Np * Kp;
+    if (total < (int64_t)N * dim) total = (int64_t)N * dim;  // layer 0 has no activation columns, only Wx
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(W, N, in_features, kh, dim, Np, Kp, Wh, Wx);
 }
 

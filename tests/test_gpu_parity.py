@@ -169,7 +169,7 @@ def test_oracle_parity_paper_shape(act, dev, precision):
         y, res = layer(q)
     Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
     bs = [l.bias.detach().cpu().numpy() for l in model.fc]
-    beta = float(model.activ.beta) if act == "swish" else 1.0
+    beta = float(model.activ.beta.detach()) if act == "swish" else 1.0
     qn = q.cpu().numpy()
     yj = jo.query_jet(grid.cpu().numpy(), qn, 0., 1., Ws, bs, act, beta)
     iv, ov, eqs = jo.rb2_equations(**kw)
@@ -297,7 +297,7 @@ def test_full_size_properties(dev, precision):
         model.fc[5].weight.zero_()
         model.fc[5].bias.copy_(torch.tensor([1.0, -2.0, 0.5, 3.0], device=dev))
         yc, jc = sp.fused_query(grid, q[:, :65536], 0., 1., list(model.fc), "softplus", None, spec=spec)
-        assert (yc - model.fc[5].bias).abs().max() < 2e-6
+        assert (yc - model.fc[5].bias).abs().max() < 1e-5   # fp32 rounding of sum_j w_j = 1, |bias| <= 3
         assert jc.abs().max() < 1e-3          # sum_j dw_j = 0 up to fp32 rounding of 1/cubesize-scaled terms
     # (3) spot check against the fp64 oracle on a slice
     torch.manual_seed(1)
