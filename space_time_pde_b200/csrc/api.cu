@@ -140,17 +140,23 @@ static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, co
     }
     P.off_vb = off;
     off = align_up(off + (size_t)(P.nvert_total > 0 ? P.nvert_total : 1) * P.ncat * sizeof(float), 256);
+    off = align_up(off, 1024);
     P.off_tc = off;
-    off = align_up(off + tc_fixed_bytes(d, P.n_layers, P.widths, P.np), 256);
+    const bool use_tc = d->precision != STPDE_PREC_FP32;
+    if (d->precision < STPDE_PREC_FP32 || d->precision > STPDE_PREC_FP16) return fail(STPDE_EINVAL, "unknown precision %d", d->precision);
+    off = align_up(off + (use_tc ? tc_fixed_bytes(P.n_layers, P.widths) : 0), 1024);
     P.fixed_bytes = off;
     const int kc = s.kc;
-    P.per_point_bytes = (size_t)P.ncorner * (4 + 4 * d->dim) + (size_t)4 * 5 * d->dim +
-                        (size_t)kc * P.ncorner * 4 * ((size_t)P.max_even + P.max_odd) +
-                        tc_per_point_bytes(d, kc, P.ncorner, P.max_even, P.max_odd);
+    P.per_point_bytes = (size_t)P.ncorner * (4 + 4 * d->dim) + (size_t)4 * 5 * d->dim;
+    if (use_tc)   // fp32 only for the last hidden layer (input of final_blend) + fp16 hi/lo planes
+        P.per_point_bytes += (size_t)kc * P.ncorner * 4 * P.np[P.n_layers - 2] +
+                             tc_per_point_bytes(P.n_layers, P.widths, kc, P.ncorner);
+    else
+        P.per_point_bytes += (size_t)kc * P.ncorner * 4 * ((size_t)P.max_even + P.max_odd);
     return STPDE_OK;
 }
 
-static size_t chunk_region_bytes(const Plan& P, int64_t pc) { return (size_t)pc * P.per_point_bytes + 16 * 256; }
+static size_t chunk_region_bytes(const Plan& P, int64_t pc) { return (size_t)pc * P.per_point_bytes + 16 * 1024; }
 
 static int64_t default_chunk_points(const Plan& P) {
     size_t budget_mb = 6144;
@@ -169,7 +175,7 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     if (P.total_pts == 0) return STPDE_OK;
     if (ws_bytes < P.fixed_bytes + chunk_region_bytes(P, 128))
         return fail(STPDE_ENOMEM, "workspace %zu B < minimum %zu B", ws_bytes, P.fixed_bytes + chunk_region_bytes(P, 128));
-    int64_t pc = (int64_t)((ws_bytes - P.fixed_bytes - 16 * 256) / P.per_point_bytes) / 128 * 128;
+    int64_t pc = (int64_t)((ws_bytes - P.fixed_bytes - 16 * 1024) / P.per_point_bytes) / 128 * 128;
     int64_t need = (P.total_pts + 127) / 128 * 128;
     if (pc > need) pc = need;
     if (pc > (1 << 24)) pc = 1 << 24;
@@ -189,9 +195,15 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     cb.wfac = (float*)take((size_t)dim * 2 * pc * 4);
     cb.dfac = (float*)take((size_t)dim * 2 * pc * 4);
     cb.dxr = (float*)take((size_t)dim * pc * 4);
-    float* act[2];
-    act[0] = (float*)take((size_t)kc * rows * P.max_even * 4);
-    act[1] = (float*)take((size_t)kc * rows * (P.max_odd > 0 ? P.max_odd : 1) * 4);
+    const bool use_tc = d->precision != STPDE_PREC_FP32;
+    float* act[2] = {nullptr, nullptr};
+    if (use_tc) {
+        act[(P.n_layers - 2) & 1] = (float*)take((size_t)kc * rows * P.np[P.n_layers - 2] * 4);
+    } else {
+        act[0] = (float*)take((size_t)kc * rows * P.max_even * 4);
+        act[1] = (float*)take((size_t)kc * rows * (P.max_odd > 0 ? P.max_odd : 1) * 4);
+    }
+    p = (char*)align_up((size_t)p, 1024);
     char* tc_chunk = p;
 
     // once per call: pack weights, per-vertex latent/bias terms
@@ -218,11 +230,10 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
     prof_end(kSlotSetup, st, P.n_layers + 1);
 
-    const bool use_tc = d->precision != STPDE_PREC_FP32;
     TcContext tc;
     if (use_tc) {
-        int rc = tc_prepare(tc, d, P.n_layers, P.widths, P.np, P.kh, P.in_features, W, ws + P.off_tc, tc_chunk,
-                            (size_t)(ws + ws_bytes - tc_chunk), P.spec, (int)pc, P.ncorner, status, st);
+        int rc = tc_prepare(tc, d->precision, P.n_layers, P.widths, P.in_features, W, ws + P.off_tc, tc_chunk,
+                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, st);
         if (rc) return fail(rc, "%s", tc_last_error());
     }
 
@@ -232,8 +243,8 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
             launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
         }
         if (use_tc) {
-            int rc = tc_run_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, (const float*)(ws + P.off_wx[0]), Vb,
-                                  P.ncat, P.cat_off, (const float* const*)nullptr, ws, P.off_wx, act[(P.n_layers - 2) & 1], st);
+            int rc = tc_run_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, ws, P.off_wx,
+                                  act[(P.n_layers - 2) & 1], P.np[P.n_layers - 2], st);
             if (rc) return fail(rc, "%s", tc_last_error());
         } else {
             {

@@ -1,0 +1,341 @@
+// tcgen05 / TMA / mbarrier primitives (inline PTX, sm_100a) and the tensor-core layer kernel.
+//
+// Layer l (1 <= l <= n-2) computes, for every jet component c and every (point, corner) row r,
+//     z[c][r][g] = sum_f W_l[g][f] * a_{l-1}[c][r][f]
+// as D[M = 128 features, N = KC * NR rows] = W_tile[128 x K] * Act_tile[N x K]^T on the 5th-gen
+// tensor cores: the WEIGHTS are the M-side operand, so a TMEM lane is one output feature and the
+// KC jet components of a row sit in neighbouring TMEM columns of the same lane - exactly what the
+// jet-activation epilogue needs in one thread.
+//
+// Precision: operands are fp16 "hi + lo" pairs (x ~= hi + lo, 22 significant bits); a product is
+// hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM (3 MMAs, STPDE_PREC_FP16X3) or hi*hi only
+// (STPDE_PREC_FP16).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stpde {
+namespace tc {
+
+constexpr int kBlockK = 64;     // fp16 elements per K block = 128 B = one swizzle-128B span
+constexpr int kTileF = 128;     // features per CTA tile (UMMA M)
+constexpr int kStages = 2;      // smem ring depth (single-CTA version; the CTA-pair version fits 3-4)
+constexpr int kThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ residual)
+
+// rows (point, corner) per tile for KC jet components: NR % 16 == 0 and KC * NR <= 256
+__host__ __device__ constexpr int rows_per_tile(int kc) {
+    return kc == 1 ? 256 : kc == 2 ? 128 : kc == 3 ? 80 : kc == 4 ? 64 : kc == 5 ? 48 : kc <= 8 ? 32 : 16;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel (error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) break;   // ~2 s: no wait in this kernel is legitimately that long
+    }
+    atomicOr(status, 0x100);
+    __trap();
+}
+
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms of 1024 B
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) with SWIZZLE_128B = 2)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32, A=B=F16, both K-major, dense
+__host__ __device__ constexpr uint32_t make_instr_desc(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct LayerArgs {
+    int rows;          // (point, corner) rows in the chunk
+    int n_feat;        // true output width of the layer
+    int kp_in;         // padded K (multiple of 64)
+    int ld_out;        // row stride of the output planes (fp16: next layer's kp_in; fp32: np)
+    int n_store;       // features >= n_store are not written; [n_feat, n_store) are written as zeros
+    int last;          // 1: write fp32 activations for final_blend, 0: write fp16 hi/lo planes
+    int passes;        // 3 = hi/lo split, 1 = single fp16 pass
+    int dim, act, ncat, cat_off;
+    float beta;
+    const float* wscale;   // device: 2^-(sw_l + sa) for this layer
+    const float* Wx;       // [n_feat][dim]
+    const float* Vb;       // [nvert][ncat]
+    const int* vtx;        // [rows]
+    const float* xrel;     // [dim][rows]
+    __half* out_hi;        // [KC][rows][ld_out]
+    __half* out_lo;
+    float* out_f32;        // [KC][rows][ld_out]
+    int* status;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                JetSpec spec, LayerArgs args) {
+    constexpr int NR = rows_per_tile(KC);
+    constexpr int N = KC * NR;
+    constexpr int NRB = NR / 8;
+    constexpr uint32_t kWBytes = kTileF * kBlockK * 2;        // one W plane tile
+    constexpr uint32_t kABytes = N * kBlockK * 2;             // one activation plane tile
+    constexpr uint32_t kStageBytes = 2 * kWBytes + 2 * kABytes;
+    constexpr uint32_t kTmemCols = 512;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tfull_bar = bars + 2 * kStages;
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_ftiles = (args.n_store + kTileF - 1) / kTileF;
+    const int n_rtiles = (args.rows + NR - 1) / NR;
+    const int n_tiles = n_ftiles * n_rtiles;
+    const int kb_count = args.kp_in / kBlockK;
+    const bool three = args.passes == 3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 128); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                    mbar_expect_tx(fb, three ? kStageBytes : (kWBytes + kABytes));
+                    tma_load_2d(base, &map_w_hi, kb * kBlockK, f0, fb);
+                    if (three) tma_load_2d(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
+#pragma unroll
+                    for (int rb = 0; rb < NRB; ++rb) {
+                        tma_load_3d(base + 2 * kWBytes + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        if (three)
+                            tma_load_3d(base + 2 * kWBytes + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK,
+                                        r0 + rb * 8, 0, fb);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_instr_desc(kTileF, N);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * N;
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t w_hi = make_smem_desc(base), w_lo = make_smem_desc(base + kWBytes);
+                    const uint64_t a_hi = make_smem_desc(base + 2 * kWBytes), a_lo = make_smem_desc(base + 2 * kWBytes + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // +32 B along K inside the swizzle span
+                        umma_f16(d_tmem, w_hi + adv, a_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        if (three) {
+                            umma_f16(d_tmem, w_hi + adv, a_lo + adv, idesc, 1u);
+                            umma_f16(d_tmem, w_lo + adv, a_hi + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem stage when the MMAs retire
+                    if (kb == kb_count - 1) umma_commit(smem_u32(&tfull_bar[buf]));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps: TMEM -> jets activation -> global =====================
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+        const float scale = *args.wscale;
+        const float act_scale = (float)(1 << kActScaleLog2);
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
+            const int g = f0 + quarter * 32 + lane;
+            float wx[kMaxDim];
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? args.Wx[g * args.dim + k] : 0.f;
+            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
+            bool overflow = false;
+#pragma unroll 1
+            for (int rb = 0; rb < NRB; ++rb) {
+                uint32_t v[KC][8];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + rb * 8 + i;
+                    if (r >= args.rows || g >= args.n_store) continue;
+                    float o[KC];
+                    if (g < args.n_feat) {
+                        float zt[KC];
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) zt[c] = __uint_as_float(v[c][i]) * scale;
+                        float z = zt[0] + args.Vb[(int64_t)args.vtx[r] * args.ncat + args.cat_off + g];
+#pragma unroll
+                        for (int k = 0; k < kMaxDim; ++k)
+                            if (k < args.dim) z = fmaf(wx[k], args.xrel[(int64_t)k * args.rows + r], z);
+                        float s0, s1, s2;
+                        act_jet(args.act, args.beta, z, s0, s1, s2);
+#pragma unroll
+                        for (int c = 1; c < KC; ++c)
+                            if (c <= spec.n_first) zt[c] += wx[spec.first_dirs[c - 1]];
+                        o[0] = s0;
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) {
+                            if (c <= spec.n_first) o[c] = s1 * zt[c];
+                            else {
+                                const int s = c - 1 - spec.n_first;
+                                float za = 0.f, zb = 0.f;
+#pragma unroll
+                                for (int cc = 1; cc < KC; ++cc) {
+                                    if (cc == spec.sec_a[s]) za = zt[cc];
+                                    if (cc == spec.sec_b[s]) zb = zt[cc];
+                                }
+                                o[c] = fmaf(s2 * za, zb, s1 * zt[c]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) o[c] = 0.f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) {
+                        const int64_t off = ((int64_t)c * args.rows + r) * args.ld_out + g;
+                        if (args.last) {
+                            args.out_f32[off] = o[c];
+                        } else {
+                            const float xs = o[c] * act_scale;
+                            overflow |= !(fabsf(xs) < 65000.f);
+                            const __half hi = __float2half_rn(xs);
+                            args.out_hi[off] = hi;
+                            if (three) args.out_lo[off] = __float2half_rn(xs - __half2float(hi));
+                        }
+                    }
+                }
+            }
+            if (overflow) atomicOr(args.status, kStatusRange);
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[buf]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace stpde

@@ -1,18 +1,317 @@
-// Placeholder until the tcgen05 kernels land: the tensor-core precisions report STPDE_EUNSUPPORTED.
+// Host orchestration + small helper kernels of the tensor-core path.
 #include "tc_path.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "profile.h"
+#include "tc_kernels.cuh"
 
 namespace stpde {
 
-size_t tc_fixed_bytes(const stpde_desc_t*, int, const int*, const int*) { return 0; }
-size_t tc_per_point_bytes(const stpde_desc_t*, int, int, int, int) { return 0; }
-int tc_prepare(TcContext&, const stpde_desc_t*, int, const int*, const int*, const int*, const int*,
-               const float* const*, char*, char*, size_t, const JetSpec&, int, int, int*, cudaStream_t) {
-    return STPDE_EUNSUPPORTED;
+static thread_local char g_tc_err[256] = "";
+const char* tc_last_error() { return g_tc_err; }
+static int tc_fail(int code, const char* msg) { snprintf(g_tc_err, sizeof(g_tc_err), "%s", msg); return code; }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// helper kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ W, int N, int in_features, int kh, unsigned* __restrict__ out) {
+    float m = 0.f;
+    const int64_t total = (int64_t)N * kh;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(e / kh), k = (int)(e % kh);
+        m = fmaxf(m, fabsf(W[(int64_t)n * in_features + k]));
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
 }
-int tc_run_chunk(TcContext&, const JetSpec&, int, int, float, const ChunkBuffers&, const float*, const float*, int,
-                 const int*, const float* const*, char*, const size_t*, float*, cudaStream_t) {
-    return STPDE_EUNSUPPORTED;
+
+// Whi/Wlo [np128][kp] = fp16 split of W[:, :kh] * 2^sw with max|W| * 2^sw in [2^13, 2^14)
+__global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_features, int kh, int np128, int kp,
+                                     const unsigned* __restrict__ absmax, float* __restrict__ wscale,
+                                     __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float amax = __uint_as_float(*absmax);
+    int e2 = 0;
+    if (amax > 0.f) frexpf(amax, &e2);           // amax = m * 2^e2, m in [0.5, 1)
+    const int sw = amax > 0.f ? 14 - e2 : 0;
+    const float up = ldexpf(1.f, sw);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *wscale = ldexpf(1.f, -(sw + tc::kActScaleLog2));
+    const int64_t total = (int64_t)np128 * kp;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(e / kp), k = (int)(e % kp);
+        float x = (n < N && k < kh) ? W[(int64_t)n * in_features + k] * up : 0.f;
+        __half h = __float2half_rn(x);
+        hi[e] = h;
+        lo[e] = __float2half_rn(x - __half2float(h));
+    }
 }
-const char* tc_last_error() { return "tensor-core path not available in this build"; }
+
+// layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero)
+template <int KC>
+__global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
+                                                             int ld, const int* __restrict__ vtx,
+                                                             const float* __restrict__ xrel, const float* __restrict__ Wx,
+                                                             const float* __restrict__ Vb, int ncat, int three,
+                                                             __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                             int* __restrict__ status) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ld) return;
+    float wx[kMaxDim];
+#pragma unroll
+    for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < dim && n < N) ? Wx[n * dim + k] : 0.f;
+    const float act_scale = (float)(1 << tc::kActScaleLog2);
+    bool overflow = false;
+    const int r0 = blockIdx.y * 16;
+    for (int r = r0; r < min(r0 + 16, rows); ++r) {
+        float o[KC];
+        if (n < N) {
+            float z = Vb[(int64_t)vtx[r] * ncat + n];
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k)
+                if (k < dim) z = fmaf(wx[k], xrel[(int64_t)k * rows + r], z);
+            float s0, s1, s2;
+            act_jet(act, beta, z, s0, s1, s2);
+            o[0] = s0;
+#pragma unroll
+            for (int c = 1; c < KC; ++c) {
+                if (c <= spec.n_first) o[c] = s1 * wx[spec.first_dirs[c - 1]];
+                else {
+                    int s = c - 1 - spec.n_first;
+                    o[c] = s2 * wx[spec.first_dirs[spec.sec_a[s] - 1]] * wx[spec.first_dirs[spec.sec_b[s] - 1]];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < KC; ++c) o[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            const int64_t off = ((int64_t)c * rows + r) * ld + n;
+            const float xs = o[c] * act_scale;
+            overflow |= !(fabsf(xs) < 65000.f);
+            const __half h = __float2half_rn(xs);
+            out_hi[off] = h;
+            if (three) out_lo[off] = __float2half_rn(xs - __half2float(h));
+        }
+    }
+    if (overflow) atomicOr(status, kStatusRange);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sizes
+// ---------------------------------------------------------------------------------------------
+size_t tc_fixed_bytes(int n_layers, const int* widths) {
+    size_t off = 1024;  // wscale + absmax
+    for (int l = 1; l <= n_layers - 2; ++l) {
+        size_t plane = (size_t)round_up(widths[l], 128) * round_up(widths[l - 1], 64) * sizeof(__half);
+        off += 2 * align_up(plane, 1024);
+    }
+    return off;
+}
+
+static void plane_lds(int n_layers, const int* widths, int& max_even, int& max_odd) {
+    max_even = max_odd = 64;
+    for (int l = 0; l <= n_layers - 3; ++l) {     // outputs that feed a tensor-core layer
+        int ld = round_up(widths[l], 64);
+        if (l % 2 == 0) max_even = ld > max_even ? ld : max_even;
+        else max_odd = ld > max_odd ? ld : max_odd;
+    }
+}
+
+size_t tc_per_point_bytes(int n_layers, const int* widths, int kc, int ncorner) {
+    int me, mo;
+    plane_lds(n_layers, widths, me, mo);
+    return (size_t)2 * kc * ncorner * ((size_t)me + mo) * sizeof(__half);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map_2d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1) {
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {d0 * sizeof(__half)};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                       uint32_t b2) {
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * sizeof(__half), d0 * d1 * sizeof(__half)};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
+               const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
+               int* status, cudaStream_t st) {
+    if (!encode_fn()) return tc_fail(STPDE_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+    if (n_layers < 3) return tc_fail(STPDE_EUNSUPPORTED, "the tensor-core path needs at least one hidden contraction");
+    memset(&tc, 0, sizeof(tc));
+    tc.n_layers = n_layers;
+    tc.kc = kc;
+    tc.rows = rows;
+    tc.passes = precision == STPDE_PREC_FP16X3 ? 3 : 1;
+    tc.status = status;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
+
+    tc.wscale = (float*)fixed_ws;
+    tc.absmax = (unsigned*)(fixed_ws + 512);
+    cudaMemsetAsync(tc.absmax, 0, 256, st);
+    size_t off = 1024;
+    int me, mo;
+    plane_lds(n_layers, widths, me, mo);
+    const size_t plane_even = (size_t)kc * rows * me * sizeof(__half), plane_odd = (size_t)kc * rows * mo * sizeof(__half);
+    if (2 * (align_up(plane_even, 1024) + align_up(plane_odd, 1024)) > chunk_bytes)
+        return tc_fail(STPDE_ENOMEM, "workspace too small for the fp16 activation planes");
+    char* p = chunk_ws;
+    tc.act[0][0] = (__half*)p; p += align_up(plane_even, 1024);
+    tc.act[0][1] = (__half*)p; p += align_up(plane_even, 1024);
+    tc.act[1][0] = (__half*)p; p += align_up(plane_odd, 1024);
+    tc.act[1][1] = (__half*)p;
+    tc.ld0 = round_up(widths[0], 64);
+    tc.n0 = widths[0];
+
+    prof_begin(kSlotSetup, st);
+    const int NR = tc::rows_per_tile(kc);
+    (void)NR;
+    for (int l = 1; l <= n_layers - 2; ++l) {
+        TcLayerPlan& L = tc.layer[l];
+        L.n_feat = widths[l];
+        L.np128 = round_up(widths[l], 128);
+        L.kp_in = round_up(widths[l - 1], 64);
+        L.last = (l == n_layers - 2);
+        L.ld_out = L.last ? round_up(widths[l], 16) : round_up(widths[l], 64);
+        L.n_store = L.ld_out;
+        const size_t plane = align_up((size_t)L.np128 * L.kp_in * sizeof(__half), 1024);
+        L.w_hi_ptr = (__half*)(fixed_ws + off); off += plane;
+        L.w_lo_ptr = (__half*)(fixed_ws + off); off += plane;
+        const int kh = widths[l - 1];
+        absmax_kernel<<<148, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, tc.absmax + l);
+        split_weights_kernel<<<148 * 4, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, L.np128, L.kp_in,
+                                                      tc.absmax + l, tc.wscale + l, L.w_hi_ptr, L.w_lo_ptr);
+        int rc = make_map_2d(&L.w_hi, L.w_hi_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
+        rc |= make_map_2d(&L.w_lo, L.w_lo_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
+        __half* in_hi = tc.act[(l - 1) & 1][0];
+        __half* in_lo = tc.act[(l - 1) & 1][1];
+        rc |= make_map_3d(&L.a_hi, in_hi, L.kp_in, rows, kc, tc::kBlockK, 8, kc);
+        rc |= make_map_3d(&L.a_lo, in_lo, L.kp_in, rows, kc, tc::kBlockK, 8, kc);
+        if (rc) { prof_end(kSlotSetup, st, 0); return tc_fail(STPDE_ECUDA, "cuTensorMapEncodeTiled failed"); }
+    }
+    prof_end(kSlotSetup, st, 2 * (n_layers - 2));
+    return STPDE_OK;
+}
+
+template <int KC>
+static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
+                        cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    constexpr int N = KC * NR;
+    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
+        configured = true;
+    }
+    const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
+    const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
+    tc::tc_layer_kernel<KC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    return STPDE_OK;
+}
+
+template <int KC>
+static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
+                             int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
+    dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 15) / 16);
+    layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
+                                                    tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
+}
+
+#define STPDE_TC_DISPATCH_KC(kc, CALL)                 \
+    switch (kc) {                                      \
+        case 1: { constexpr int KC = 1; CALL; } break; \
+        case 2: { constexpr int KC = 2; CALL; } break; \
+        case 3: { constexpr int KC = 3; CALL; } break; \
+        case 4: { constexpr int KC = 4; CALL; } break; \
+        case 5: { constexpr int KC = 5; CALL; } break; \
+        case 6: { constexpr int KC = 6; CALL; } break; \
+        case 7: { constexpr int KC = 7; CALL; } break; \
+        case 8: { constexpr int KC = 8; CALL; } break; \
+        case 9: { constexpr int KC = 9; CALL; } break; \
+        default: { constexpr int KC = 10; CALL; } break; \
+    }
+
+int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
+                 const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
+                 int np_last, cudaStream_t st) {
+    if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_prepare");
+    {
+        ProfScope ps(kSlotLayer0, st);
+        STPDE_TC_DISPATCH_KC(spec.kc, launch_layer0_tc<KC>(tc, spec, dim, act, beta, cb, tc.n0,
+                                                           (const float*)(ws + off_wx[0]), Vb, ncat, st));
+    }
+    for (int l = 1; l <= tc.n_layers - 2; ++l) {
+        const TcLayerPlan& L = tc.layer[l];
+        tc::LayerArgs a;
+        memset(&a, 0, sizeof(a));
+        a.rows = cb.rows;
+        a.n_feat = L.n_feat;
+        a.kp_in = L.kp_in;
+        a.ld_out = L.last ? np_last : L.ld_out;
+        a.n_store = a.ld_out;
+        a.last = L.last;
+        a.passes = tc.passes;
+        a.dim = dim;
+        a.act = act;
+        a.ncat = ncat;
+        a.cat_off = cat_off[l];
+        a.beta = beta;
+        a.wscale = tc.wscale + l;
+        a.Wx = (const float*)(ws + off_wx[l]);
+        a.Vb = Vb;
+        a.vtx = cb.vtx;
+        a.xrel = cb.xrel;
+        a.out_hi = tc.act[l & 1][0];
+        a.out_lo = tc.act[l & 1][1];
+        a.out_f32 = act_last;
+        a.status = tc.status;
+        int rc = STPDE_OK;
+        ProfScope ps(kSlotGemm + l - 1, st);
+        STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer<KC>(tc, L, spec, a, st));
+        if (rc) return rc;
+    }
+    return STPDE_OK;
+}
 
 }  // namespace stpde

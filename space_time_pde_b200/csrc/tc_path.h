@@ -1,5 +1,7 @@
-// tcgen05 tensor-core path (fp16 hi/lo split operands, fp32 accumulation in TMEM).
+// Host side of the tcgen05 tensor-core path (fp16 hi/lo split operands, fp32 accumulation in TMEM).
 #pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -7,18 +9,37 @@
 
 namespace stpde {
 
-struct TcContext {
-    void* impl[64];
+struct TcLayerPlan {
+    int n_feat, np128, kp_in, ld_out, n_store, last, cat_off;
+    CUtensorMap w_hi, w_lo, a_hi, a_lo;
+    __half *w_hi_ptr, *w_lo_ptr;
 };
 
-size_t tc_fixed_bytes(const stpde_desc_t* d, int n_layers, const int* widths, const int* np);
-size_t tc_per_point_bytes(const stpde_desc_t* d, int kc, int ncorner, int max_even, int max_odd);
-int tc_prepare(TcContext& tc, const stpde_desc_t* d, int n_layers, const int* widths, const int* np, const int* kh,
-               const int* in_features, const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes,
-               const JetSpec& spec, int pc, int ncorner, int* status, cudaStream_t st);
+struct TcContext {
+    int n_layers, kc, rows, passes, num_sms;
+    TcLayerPlan layer[kMaxLayers];     // hidden layers 1..n_layers-2
+    __half* act[2][2];                 // [buffer parity][hi/lo] planes [KC][rows][ld]
+    int ld0, n0;                       // row stride / true width of layer 0's output planes
+    float* wscale;                     // device [kMaxLayers]
+    unsigned* absmax;                  // device [kMaxLayers]
+    int* status;
+};
+
+// bytes of the call-invariant region (split weights, scales) and of the per-point activation planes
+size_t tc_fixed_bytes(int n_layers, const int* widths);
+size_t tc_per_point_bytes(int n_layers, const int* widths, int kc, int ncorner);
+
+// Once per call: split the hidden-layer weights into scaled fp16 hi/lo planes, build the TMA maps.
+int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
+               const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
+               int* status, cudaStream_t st);
+
+// Per chunk: layer 0 (closed form) -> hidden layers on the tensor cores; the last hidden layer's
+// activations are written as fp32 [KC][rows][np_last] into act_last for final_blend.
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
-                 const float* Wx0, const float* Vb, int ncat, const int* cat_off, const float* const* unused,
-                 char* ws, const size_t* off_wx, float* act_last, cudaStream_t st);
+                 const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
+                 int np_last, cudaStream_t st);
+
 const char* tc_last_error();
 
 }  // namespace stpde

@@ -28,10 +28,18 @@ def dev():
     return torch.device("cuda:0")
 
 
+# fp32 (FFMA) and fp16x3 (split-precision tensor cores) are parity modes: 1e-5.  fp16 is the single-pass
+# relaxed mode of BASELINE config 3 (fp16 operands carry 11 bits): 5e-3.
+TOLS = {"fp32": 1e-5, "fp16x3": 1e-5, "fp16": 5e-3}
+
+
 @pytest.fixture(params=PRECISIONS)
 def precision(request):
+    global TOL
     jets.set_default_precision(request.param)
+    TOL = TOLS[request.param]
     yield request.param
+    TOL = 1e-5
     jets.set_default_precision("fp32")
 
 
