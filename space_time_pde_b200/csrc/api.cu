@@ -124,6 +124,10 @@ static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, co
         s.sec_a[i] = ca;
         s.sec_b[i] = cb;
     }
+    for (int c = 1; c < s.kc; ++c) {
+        if (c <= s.n_first) { s.kind[c] = 1; s.dir[c] = s.first_dirs[c - 1]; }
+        else { s.kind[c] = 2; s.pa[c] = s.sec_a[c - 1 - s.n_first]; s.pb[c] = s.sec_b[c - 1 - s.n_first]; }
+    }
     // fixed workspace region
     size_t off = 256;  // status / scratch words
     for (int l = 0; l < P.n_layers; ++l) {

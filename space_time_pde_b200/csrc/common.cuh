@@ -26,6 +26,13 @@ struct JetSpec {
     int first_dirs[STPDE_MAX_FIRST];
     int sec_a[STPDE_MAX_SECOND];  // component index of d/dx_i
     int sec_b[STPDE_MAX_SECOND];  // component index of d/dx_j
+    // per-component view (indexed by the component, so fully unrolled kernels read these straight
+    // from the constant bank): kind 0 = value, 1 = first order along dir, 2 = second order with
+    // first-order parent components pa, pb
+    int kind[STPDE_MAX_COMPONENTS];
+    int dir[STPDE_MAX_COMPONENTS];
+    int pa[STPDE_MAX_COMPONENTS];
+    int pb[STPDE_MAX_COMPONENTS];
 };
 
 // Geometry of the latent grid and the clip / cell arithmetic, all float32 exactly as the

@@ -25,7 +25,9 @@ namespace tc {
 constexpr int kBlockK = 64;     // fp16 elements per K block = 128 B = one swizzle-128B span
 constexpr int kTileF = 128;     // features per CTA tile (UMMA M)
 constexpr int kStages = 2;      // smem ring depth (single-CTA version; the CTA-pair version fits 3-4)
-constexpr int kThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kEpiWarps = 16;   // epilogue warps (4 per TMEM lane quarter, interleaved over the 8-row blocks)
+constexpr int kEpiPerQuarter = kEpiWarps / 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ residual)
 
 // rows (point, corner) per tile for KC jet components: NR % 16 == 0 and KC * NR <= 256
@@ -185,7 +187,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 128); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 32 * kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -254,80 +256,98 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
         }
     } else {
         // ===================== epilogue warps: TMEM -> jets activation -> global =====================
-        const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
-        const float scale = *args.wscale;
+        // Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter alternate 8-row blocks.
+        const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const float scale = __ldg(args.wscale);
         const float act_scale = (float)(1 << kActScaleLog2);
+        // skip connection + per-vertex latent/bias term of one 8-row block (independent loads, issued early)
+        auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = min(r_base + i, args.rows - 1);
+                float z = (g < args.n_feat) ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + r) * args.ncat + args.cat_off + g) : 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (k < args.dim) z = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + r), z);
+                zs[i] = z;
+            }
+        };
+        const int64_t plane = (int64_t)args.rows * args.ld_out;   // elements between jet components
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
             const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
             const int g = f0 + quarter * 32 + lane;
+            const bool g_store = g < args.n_store;
+            const float fmask = g < args.n_feat ? 1.f : 0.f;       // pad features are written as zeros
             float wx[kMaxDim];
 #pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? args.Wx[g * args.dim + k] : 0.f;
+            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+            float wxc[KC];                                          // constant tangent seed of first-order components
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                wxc[c] = 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+            }
+            float zs[8];
+            if (sub < NRB) load_skip(r0 + sub * 8, g, wx, zs);
             mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            bool overflow = false;
+            float amax = 0.f;
 #pragma unroll 1
-            for (int rb = 0; rb < NRB; ++rb) {
+            for (int rb = sub; rb < NRB; rb += kEpiPerQuarter) {
                 uint32_t v[KC][8];
 #pragma unroll
                 for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
+                float zs_next[8];
+                if (rb + kEpiPerQuarter < NRB) load_skip(r0 + (rb + kEpiPerQuarter) * 8, g, wx, zs_next);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = r0 + rb * 8 + i;
-                    if (r >= args.rows || g >= args.n_store) continue;
-                    float o[KC];
-                    if (g < args.n_feat) {
-                        float zt[KC];
+                    float zt[KC], o[KC];
 #pragma unroll
-                        for (int c = 0; c < KC; ++c) zt[c] = __uint_as_float(v[c][i]) * scale;
-                        float z = zt[0] + args.Vb[(int64_t)args.vtx[r] * args.ncat + args.cat_off + g];
+                    for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
+                    float s0, s1, s2;
+                    act_jet(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    o[0] = s0 * fmask;
+                    s1 *= fmask;
+                    s2 *= fmask;
 #pragma unroll
-                        for (int k = 0; k < kMaxDim; ++k)
-                            if (k < args.dim) z = fmaf(wx[k], args.xrel[(int64_t)k * args.rows + r], z);
-                        float s0, s1, s2;
-                        act_jet(args.act, args.beta, z, s0, s1, s2);
+                    for (int c = 1; c < KC; ++c) {
+                        float za = 0.f, zb = 0.f;
 #pragma unroll
-                        for (int c = 1; c < KC; ++c)
-                            if (c <= spec.n_first) zt[c] += wx[spec.first_dirs[c - 1]];
-                        o[0] = s0;
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) {
-                            if (c <= spec.n_first) o[c] = s1 * zt[c];
-                            else {
-                                const int s = c - 1 - spec.n_first;
-                                float za = 0.f, zb = 0.f;
-#pragma unroll
-                                for (int cc = 1; cc < KC; ++cc) {
-                                    if (cc == spec.sec_a[s]) za = zt[cc];
-                                    if (cc == spec.sec_b[s]) zb = zt[cc];
-                                }
-                                o[c] = fmaf(s2 * za, zb, s1 * zt[c]);
-                            }
+                        for (int cc = 1; cc < KC; ++cc) {
+                            if (spec.kind[c] == 2 && cc == spec.pa[c]) za = zt[cc];
+                            if (spec.kind[c] == 2 && cc == spec.pb[c]) zb = zt[cc];
                         }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < KC; ++c) o[c] = 0.f;
+                        o[c] = fmaf(s2 * za, zb, s1 * zt[c]);    // first order: za = zb = 0
                     }
-#pragma unroll
-                    for (int c = 0; c < KC; ++c) {
-                        const int64_t off = ((int64_t)c * args.rows + r) * args.ld_out + g;
+                    if (g_store && r < args.rows) {
+                        const int64_t off = (int64_t)r * args.ld_out + g;
                         if (args.last) {
-                            args.out_f32[off] = o[c];
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) args.out_f32[off + c * plane] = o[c];
                         } else {
-                            const float xs = o[c] * act_scale;
-                            overflow |= !(fabsf(xs) < 65000.f);
-                            const __half hi = __float2half_rn(xs);
-                            args.out_hi[off] = hi;
-                            if (three) args.out_lo[off] = __float2half_rn(xs - __half2float(hi));
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) {
+                                const float xs = o[c] * act_scale;
+                                amax = fmaxf(amax, fabsf(xs));
+                                const __half hi = __float2half_rn(xs);
+                                args.out_hi[off + c * plane] = hi;
+                                if (three) args.out_lo[off + c * plane] = __float2half_rn(xs - __half2float(hi));
+                            }
                         }
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
             }
-            if (overflow) atomicOr(args.status, kStatusRange);
+            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
             tc_fence_before();
             mbar_arrive(smem_u32(&tempty_bar[buf]));
         }

@@ -50,7 +50,8 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
     }
 }
 
-// layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero)
+// layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
+// One thread = 8 consecutive features of one row: 16-byte stores, coalesced 512 B per warp and plane.
 template <int KC>
 __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
                                                              int ld, const int* __restrict__ vtx,
@@ -58,47 +59,83 @@ __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int d
                                                              const float* __restrict__ Vb, int ncat, int three,
                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                              int* __restrict__ status) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= ld) return;
-    float wx[kMaxDim];
+    const int fg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int n0 = (blockIdx.x * 32 + fg) * 8;
+    if (n0 >= ld) return;
+    float wx[8][kMaxDim];
 #pragma unroll
-    for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < dim && n < N) ? Wx[n * dim + k] : 0.f;
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k) wx[e][k] = (k < dim && n0 + e < N) ? __ldg(Wx + (n0 + e) * dim + k) : 0.f;
     const float act_scale = (float)(1 << tc::kActScaleLog2);
-    bool overflow = false;
-    const int r0 = blockIdx.y * 16;
-    for (int r = r0; r < min(r0 + 16, rows); ++r) {
-        float o[KC];
-        if (n < N) {
-            float z = Vb[(int64_t)vtx[r] * ncat + n];
+    // per-feature constants of the closed-form layer-0 jets (row independent): a_c = sigma^(order) * coef[c]
+    float coef[KC][8];
 #pragma unroll
-            for (int k = 0; k < kMaxDim; ++k)
-                if (k < dim) z = fmaf(wx[k], xrel[(int64_t)k * rows + r], z);
-            float s0, s1, s2;
-            act_jet(act, beta, z, s0, s1, s2);
-            o[0] = s0;
+    for (int e = 0; e < 8; ++e) {
+        const float fm = (n0 + e < N) ? act_scale : 0.f;      // pad features -> 0; fold the fp16 scale in
+        coef[0][e] = fm;
 #pragma unroll
-            for (int c = 1; c < KC; ++c) {
-                if (c <= spec.n_first) o[c] = s1 * wx[spec.first_dirs[c - 1]];
-                else {
-                    int s = c - 1 - spec.n_first;
-                    o[c] = s2 * wx[spec.first_dirs[spec.sec_a[s] - 1]] * wx[spec.first_dirs[spec.sec_b[s] - 1]];
-                }
+        for (int c = 1; c < KC; ++c) {
+            float wa = 1.f, wb = 1.f;
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) {
+                if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[e][k];
+                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[e][k];
+                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[e][k];
             }
+            coef[c][e] = wa * wb * fm;
+        }
+    }
+    float amax = 0.f;
+    const bool vec_ok = (n0 + 8 <= N) && (ncat % 4 == 0);
+    for (int j = 0; j < 8; ++j) {
+        const int r = blockIdx.y * 64 + rl + 8 * j;
+        if (r >= rows) break;
+        float xr[kMaxDim];
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k) xr[k] = k < dim ? __ldg(xrel + (int64_t)k * rows + r) : 0.f;
+        const float* vrow = Vb + (int64_t)__ldg(vtx + r) * ncat + n0;
+        float vb[8];
+        if (vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(vrow));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(vrow) + 1);
+            vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w; vb[4] = b.x; vb[5] = b.y; vb[6] = b.z; vb[7] = b.w;
         } else {
 #pragma unroll
-            for (int c = 0; c < KC; ++c) o[c] = 0.f;
+            for (int e = 0; e < 8; ++e) vb[e] = (n0 + e < N) ? __ldg(vrow + e) : 0.f;
+        }
+        float o[KC][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float z = vb[e];
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k)
+                if (k < dim) z = fmaf(wx[e][k], xr[k], z);
+            float s0, s1, s2;
+            act_jet(act, beta, z, s0, s1, s2);
+            o[0][e] = s0 * coef[0][e];
+#pragma unroll
+            for (int c = 1; c < KC; ++c) o[c][e] = (spec.kind[c] == 1 ? s1 : s2) * coef[c][e];
         }
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
-            const int64_t off = ((int64_t)c * rows + r) * ld + n;
-            const float xs = o[c] * act_scale;
-            overflow |= !(fabsf(xs) < 65000.f);
-            const __half h = __float2half_rn(xs);
-            out_hi[off] = h;
-            if (three) out_lo[off] = __float2half_rn(xs - __half2float(h));
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const float x0 = o[c][e], x1 = o[c][e + 1];
+                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const int64_t off = ((int64_t)c * rows + r) * ld + n0;
+            *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (three) *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
     }
-    if (overflow) atomicOr(status, kStatusRange);
+    if (!(amax < 65000.f)) atomicOr(status, kStatusRange);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -253,7 +290,7 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
 template <int KC>
 static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
-    dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 15) / 16);
+    dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 63) / 64);
     layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
                                                     tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
 }

@@ -1,0 +1,24 @@
+"""One forward + residual pass at BASELINE config[1] shapes (fewer points) for ncu captures."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import space_time_pde_b200 as sp
+from space_time_pde_b200 import jets
+
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
+npts = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+jets.set_default_precision(precision)
+dev = torch.device("cuda:0")
+model = bench.make_model(dev)
+grid, q = bench.synthetic_inputs(1234, dev, npts)
+layer = sp.get_rb2_pde_layer(**bench.RB2)
+layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+for _ in range(2):
+    with torch.no_grad():
+        y, res = layer(q)
+torch.cuda.synchronize()
+print("ok", float(y.abs().mean()))
