@@ -46,25 +46,34 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded spin: a protocol bug must surface as a trapped kernel (error), never as a hung GPU.
+// Wait for a barrier phase.  try_wait carries a suspend-time hint so the warp SLEEPS in hardware until the
+// phase completes (a hot spin loop here steals issue slots from the single TMA / MMA issuing threads).
+// Bounded: a protocol bug must surface as a trapped kernel (error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status) {
     uint32_t done = 0;
-    const long long t0 = clock64();
-    while (true) {
+    for (int spin = 0; spin < 400; ++spin) {                      // 400 x <= 10 ms
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000LL) break;   // ~2 s: no wait in this kernel is legitimately that long
     }
     atomicOr(status, 0x100);
     __trap();
 }
 
+// One lane of a fully converged warp (always the same one).  The single-thread tcgen05 / TMA instructions are
+// issued under this predicate while the surrounding control flow stays warp-uniform, so descriptors and
+// addresses live in uniform registers (a divergent "if (lane == 0)" region costs ~250 scalar fix-up
+// instructions per K block and throttles the MMA issue rate).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -199,15 +208,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-                for (int kb = 0; kb < kb_count; ++kb) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    const uint32_t base = smem_u32(smem + stage * kStageBytes);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
+            for (int kb = 0; kb < kb_count; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                if (elect_one()) {
                     mbar_expect_tx(fb, three ? kStageBytes : (kWBytes + kABytes));
                     tma_load_2d(base, &map_w_hi, kb * kBlockK, f0, fb);
                     if (three) tma_load_2d(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
@@ -218,27 +227,28 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                             tma_load_3d(base + 2 * kWBytes + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK,
                                         r0 + rb * 8, 0, fb);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_instr_desc(kTileF, N);
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = make_instr_desc(kTileF, N);
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * N;
+            for (int kb = 0; kb < kb_count; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * N;
-                for (int kb = 0; kb < kb_count; ++kb) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t w_hi = make_smem_desc(base), w_lo = make_smem_desc(base + kWBytes);
-                    const uint64_t a_hi = make_smem_desc(base + 2 * kWBytes), a_lo = make_smem_desc(base + 2 * kWBytes + kABytes);
+                const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                const uint64_t w_hi = make_smem_desc(base), w_lo = make_smem_desc(base + kWBytes);
+                const uint64_t a_hi = make_smem_desc(base + 2 * kWBytes), a_lo = make_smem_desc(base + 2 * kWBytes + kABytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // +32 B along K inside the swizzle span
@@ -250,8 +260,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem stage when the MMAs retire
                     if (kb == kb_count - 1) umma_commit(smem_u32(&tfull_bar[buf]));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -355,6 +366,288 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+
+// =============================================================================================
+// CTA-pair version (cta_group::2): two SMs of a cluster share one 256-feature x N tile.
+//   * each CTA TMA-loads its own 128 weight rows and its own HALF of the activation rows, so the
+//     per-SM operand traffic and smem footprint drop (4+ pipeline stages instead of 2);
+//   * the leader CTA (cluster rank 0) issues every tcgen05.mma.cta_group::2 (M = 256); the
+//     accumulator rows 0..127 land in the leader's TMEM, rows 128..255 in the peer's;
+//   * full barriers live in the leader (both CTAs' TMA traffic completes on them), empty / tmem-full
+//     barriers are multicast to both CTAs by tcgen05.commit, tmem-empty arrivals go to the leader.
+// =============================================================================================
+constexpr int kPairMaxStages = 8;
+constexpr uint32_t kPairSmemBudget = 224 * 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     JetSpec spec, LayerArgs args) {
+    constexpr int NR = rows_per_tile(KC);
+    constexpr int N = KC * NR;
+    constexpr int NRB = NR / 8;
+    static_assert(NRB % 2 == 0, "each CTA of the pair loads half of the 8-row blocks");
+    constexpr int kTileF2 = 2 * kTileF;
+    constexpr uint32_t kWBytes = kTileF * kBlockK * 2;          // one W plane tile of this CTA (128 rows)
+    constexpr uint32_t kABytes = (N / 2) * kBlockK * 2;         // this CTA's half of one activation plane tile
+    constexpr uint32_t kTmemCols = 512;
+    const bool three = args.passes == 3;
+    const uint32_t stage_bytes = three ? 2 * kWBytes + 2 * kABytes : kWBytes + kABytes;
+    const int n_stages = min((int)(kPairSmemBudget / stage_bytes), kPairMaxStages);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + kPairSmemBudget);
+    uint64_t* full_bar = bars;                                  // used in the leader only
+    uint64_t* empty_bar = bars + kPairMaxStages;                // one copy per CTA
+    uint64_t* tfull_bar = bars + 2 * kPairMaxStages;            // one copy per CTA
+    uint64_t* tempty_bar = bars + 2 * kPairMaxStages + 2;       // used in the leader only
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kPairMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_ftiles = (args.n_store + kTileF2 - 1) / kTileF2;
+    const int n_rtiles = (args.rows + NR - 1) / NR;
+    const int n_tiles = n_ftiles * n_rtiles;
+    const int kb_count = args.kp_in / kBlockK;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kPairMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (warp-uniform loop; one elected lane per CTA issues) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = pair_id; t < n_tiles; t += n_pairs) {
+            const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF;
+            const int r0 = (t / n_ftiles) * NR + (int)rank * (NR / 2);
+            for (int kb = 0; kb < kb_count; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);   // the leader's copy of the barrier
+                const uint32_t base = smem_u32(smem + stage * stage_bytes);
+                const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * stage_bytes);   // bytes of BOTH CTAs
+                    tma_load_2d_pair(base, &map_w_hi, kb * kBlockK, f0, fb);
+                    if (three) tma_load_2d_pair(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
+#pragma unroll
+                    for (int rb = 0; rb < NRB / 2; ++rb) {
+                        tma_load_3d_pair(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        if (three)
+                            tma_load_3d_pair(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
+                    }
+                }
+                __syncwarp();
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: leader CTA, warp-uniform loop, one elected lane issues =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_instr_desc(kTileF2, N);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
+                const int buf = it & 1;
+                mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * N;
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
+                    const uint64_t w_hi = make_smem_desc(base), w_lo = make_smem_desc(base + kWBytes);
+                    const uint64_t a_hi = make_smem_desc(a_base), a_lo = make_smem_desc(a_base + kABytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_f16_pair(d_tmem, w_hi + adv, a_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            if (three) {
+                                umma_f16_pair(d_tmem, w_hi + adv, a_lo + adv, idesc, 1u);
+                                umma_f16_pair(d_tmem, w_lo + adv, a_hi + adv, idesc, 1u);
+                            }
+                        }
+                        umma_commit_pair(smem_u32(&empty_bar[stage]));
+                        if (kb == kb_count - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));
+                    }
+                    __syncwarp();
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
+        const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const float scale = __ldg(args.wscale);
+        const float act_scale = (float)(1 << kActScaleLog2);
+        auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = min(r_base + i, args.rows - 1);
+                float z = (g < args.n_feat) ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + r) * args.ncat + args.cat_off + g) : 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (k < args.dim) z = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + r), z);
+                zs[i] = z;
+            }
+        };
+        const int64_t plane = (int64_t)args.rows * args.ld_out;
+        const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
+        int it = 0;
+        for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
+            const int buf = it & 1;
+            const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
+            const int g = f0 + quarter * 32 + lane;
+            const bool g_store = g < args.n_store;
+            const float fmask = g < args.n_feat ? 1.f : 0.f;
+            float wx[kMaxDim];
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+            float wxc[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                wxc[c] = 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+            }
+            float zs[8];
+            if (sub < NRB) load_skip(r0 + sub * 8, g, wx, zs);
+            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
+            float amax = 0.f;
+#pragma unroll 1
+            for (int rb = sub; rb < NRB; rb += kEpiPerQuarter) {
+                uint32_t v[KC][8];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
+                float zs_next[8];
+                if (rb + kEpiPerQuarter < NRB) load_skip(r0 + (rb + kEpiPerQuarter) * 8, g, wx, zs_next);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + rb * 8 + i;
+                    float zt[KC], o[KC];
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
+                    float s0, s1, s2;
+                    act_jet(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    o[0] = s0 * fmask;
+                    s1 *= fmask;
+                    s2 *= fmask;
+#pragma unroll
+                    for (int c = 1; c < KC; ++c) {
+                        float za = 0.f, zb = 0.f;
+#pragma unroll
+                        for (int cc = 1; cc < KC; ++cc) {
+                            if (spec.kind[c] == 2 && cc == spec.pa[c]) za = zt[cc];
+                            if (spec.kind[c] == 2 && cc == spec.pb[c]) zb = zt[cc];
+                        }
+                        o[c] = fmaf(s2 * za, zb, s1 * zt[c]);
+                    }
+                    if (g_store && r < args.rows) {
+                        const int64_t off = (int64_t)r * args.ld_out + g;
+                        if (args.last) {
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) args.out_f32[off + c * plane] = o[c];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) {
+                                const float xs = o[c] * act_scale;
+                                amax = fmaxf(amax, fabsf(xs));
+                                const __half hi = __float2half_rn(xs);
+                                args.out_hi[off + c * plane] = hi;
+                                if (three) args.out_lo[off + c * plane] = __float2half_rn(xs - __half2float(hi));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
+            }
+            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 }  // namespace tc

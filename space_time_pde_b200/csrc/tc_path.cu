@@ -2,6 +2,7 @@
 #include "tc_path.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "profile.h"
@@ -218,6 +219,8 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.rows = rows;
     tc.passes = precision == STPDE_PREC_FP16X3 ? 3 : 1;
     tc.status = status;
+    const char* pair_env = getenv("STPDE_TC_PAIR");
+    tc.use_pair = pair_env ? atoi(pair_env) : 1;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -288,6 +291,24 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
 }
 
 template <int KC>
+static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
+                             cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
+        configured = true;
+    }
+    const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
+    const int max_pairs = tc.num_sms / 2;
+    const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
+    tc::tc_layer_pair_kernel<KC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    return STPDE_OK;
+}
+
+template <int KC>
 static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
     dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 63) / 64);
@@ -345,7 +366,11 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         a.status = tc.status;
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
-        STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer<KC>(tc, L, spec, a, st));
+        if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
+            STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer_pair<KC>(tc, L, spec, a, st));
+        } else {
+            STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer<KC>(tc, L, spec, a, st));
+        }
         if (rc) return rc;
     }
     return STPDE_OK;

@@ -16,7 +16,7 @@ struct TcLayerPlan {
 };
 
 struct TcContext {
-    int n_layers, kc, rows, passes, num_sms;
+    int n_layers, kc, rows, passes, num_sms, use_pair;
     TcLayerPlan layer[kMaxLayers];     // hidden layers 1..n_layers-2
     __half* act[2][2];                 // [buffer parity][hi/lo] planes [KC][rows][ld]
     int ld0, n0;                       // row stride / true width of layer 0's output planes
