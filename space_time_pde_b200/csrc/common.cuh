@@ -92,4 +92,53 @@ __device__ __forceinline__ void act_jet(int kind, float beta, float z, float& s0
     }
 }
 
+// Same functions with MUFU-based exp / log / reciprocal (absolute error ~1e-7 .. 4e-7, i.e. the size of the
+// 2^-22 operand rounding the split-precision tensor-core path already carries).  Used by the tensor-core
+// kernels only; the FP32 path keeps the libdevice-accurate versions above.
+__device__ __forceinline__ void act_jet_fast(int kind, float beta, float z, float& s0, float& s1, float& s2) {
+    switch (kind) {
+        case STPDE_ACT_TANH: {
+            const float e = __expf(2.f * z);                 // tanh z = 1 - 2 / (1 + e^{2z})
+            const float t = 1.f - __fdividef(2.f, 1.f + e);
+            const float u = 1.f - t * t;
+            s0 = t; s1 = u; s2 = -2.f * t * u;
+            break;
+        }
+        case STPDE_ACT_RELU: {
+            const bool p = z > 0.f;
+            s0 = p ? z : 0.f; s1 = p ? 1.f : 0.f; s2 = 0.f;
+            break;
+        }
+        case STPDE_ACT_LEAKYRELU: {
+            const bool p = z > 0.f;
+            s0 = p ? z : 0.01f * z; s1 = p ? 1.f : 0.01f; s2 = 0.f;
+            break;
+        }
+        case STPDE_ACT_SOFTPLUS: {
+            const bool lin = z > 20.f;
+            const float e = __expf(fminf(z, 20.f));
+            const float w = 1.f + e;
+            const float r = __fdividef(1.f, w);
+            const float s = e * r;
+            s0 = lin ? z : __logf(w);
+            s1 = lin ? 1.f : s;
+            s2 = lin ? 0.f : s * r;                           // s (1 - s) = s / (1 + e)
+            break;
+        }
+        case STPDE_ACT_ELU: {
+            const bool neg = z <= 0.f;
+            const float e = __expf(fminf(z, 0.f));
+            s0 = neg ? e - 1.f : z; s1 = neg ? e : 1.f; s2 = neg ? e : 0.f;
+            break;
+        }
+        default: {  // STPDE_ACT_SWISH
+            const float bz = beta * z;
+            const float s = __fdividef(1.f, 1.f + __expf(-bz));
+            const float ds = s * (1.f - s);
+            s0 = z * s; s1 = s + bz * ds; s2 = beta * ds * (2.f + bz * (1.f - 2.f * s));
+            break;
+        }
+    }
+}
+
 }  // namespace stpde

@@ -448,30 +448,44 @@ __global__ void __launch_bounds__(256) final_blend_kernel(JetSpec spec, int dim,
     const int row0 = blockIdx.x * 128;
     for (int e = threadIdx.x; e < O * Kp; e += blockDim.x) Ws[e] = Wlast[e];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int rr = warp; rr < KC * 128; rr += 8) {
-        const int c = rr / 128, lr = rr % 128;
-        const int r = row0 + lr;
+    // last linear layer: stage a [128 rows x 128 k] tile in smem (coalesced 512 B row segments), then two
+    // threads per row accumulate the O dot products (row stride 129 floats -> conflict-free column walks)
+    float* tile = outc + KC * 128 * O;   // [128][129]
+    float* part = tile + 128 * 129;      // [128][kMaxOut] partial sums of the upper k half
+    const int lr = threadIdx.x & 127, kh = threadIdx.x >> 7;
+    for (int c = 0; c < KC; ++c) {
         float acc[kMaxOut];
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
-        if (r < rows) {
-            const float* a = actIn + ((int64_t)c * rows + r) * Kp;
-            for (int k = lane; k < Kp; k += 32) {
-                float av = a[k];
+        for (int k0 = 0; k0 < Kp; k0 += 128) {
+            const int kw = min(128, Kp - k0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {       // 128 rows x 32 float4
+                const int rr = e >> 5, q4 = (e & 31) * 4;
+                const int r = row0 + rr;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows && q4 < kw) v = *reinterpret_cast<const float4*>(actIn + ((int64_t)c * rows + r) * Kp + k0 + q4);
+                float* dst = tile + rr * 129 + q4;
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+            }
+            __syncthreads();
+            const int kbeg = kh * 64, kend = min(kbeg + 64, kw);
+            for (int k = kbeg; k < kend; ++k) {
+                const float av = tile[lr * 129 + k];
 #pragma unroll
                 for (int o = 0; o < kMaxOut; ++o)
-                    if (o < O) acc[o] = fmaf(av, Ws[o * Kp + k], acc[o]);
+                    if (o < O) acc[o] = fmaf(av, Ws[o * Kp + k0 + k], acc[o]);
             }
         }
+        if (kh == 1) {
 #pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) {
-            if (o < O) {
-                float v = acc[o];
+            for (int o = 0; o < kMaxOut; ++o) part[lr * kMaxOut + o] = acc[o];
+        }
+        __syncthreads();
+        if (kh == 0) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) outc[(c * 128 + lr) * O + o] = v + (c == 0 ? blast[o] : 0.f);
-            }
+            for (int o = 0; o < kMaxOut; ++o)
+                if (o < O) outc[(c * 128 + lr) * O + o] = acc[o] + part[lr * kMaxOut + o] + (c == 0 ? blast[o] : 0.f);
         }
     }
     __syncthreads();
@@ -657,7 +671,7 @@ template <int KC>
 static void launch_final_t(const JetSpec& spec, int dim, int rows, int pc, int64_t total_pts, int64_t p0, int Kp,
                            int O, const float* actIn, const float* Wlast, const float* blast,
                            const ChunkBuffers& cb, float* y, float* jets, cudaStream_t st) {
-    size_t smem = (size_t)(O * Kp + KC * 128 * O) * sizeof(float);
+    size_t smem = (size_t)(O * Kp + KC * 128 * O + 128 * 129 + 128 * kMaxOut) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(final_blend_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

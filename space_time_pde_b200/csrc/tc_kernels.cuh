@@ -324,7 +324,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
 #pragma unroll
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
-                    act_jet(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    act_jet_fast(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;
@@ -605,7 +605,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
 #pragma unroll
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
-                    act_jet(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    act_jet_fast(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;

@@ -54,7 +54,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
 // One thread = 8 consecutive features of one row: 16-byte stores, coalesced 512 B per warp and plane.
 template <int KC>
-__global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
+__global__ void __launch_bounds__(256, 2) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
                                                              int ld, const int* __restrict__ vtx,
                                                              const float* __restrict__ xrel, const float* __restrict__ Wx,
                                                              const float* __restrict__ Vb, int ncat, int three,
@@ -87,7 +87,11 @@ __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int d
             coef[c][e] = wa * wb * fm;
         }
     }
-    float amax = 0.f;
+    float cmax = 0.f, smax = 0.f;      // overflow guard: |a_c| <= max|sigma^(k)| * max|coef|
+#pragma unroll
+    for (int c = 0; c < KC; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cmax = fmaxf(cmax, fabsf(coef[c][e]));
     const bool vec_ok = (n0 + 8 <= N) && (ncat % 4 == 0);
     for (int j = 0; j < 8; ++j) {
         const int r = blockIdx.y * 64 + rl + 8 * j;
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int d
             for (int k = 0; k < kMaxDim; ++k)
                 if (k < dim) z = fmaf(wx[e][k], xr[k], z);
             float s0, s1, s2;
-            act_jet(act, beta, z, s0, s1, s2);
+            act_jet_fast(act, beta, z, s0, s1, s2);
+            smax = fmaxf(smax, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))));
             o[0][e] = s0 * coef[0][e];
 #pragma unroll
             for (int c = 1; c < KC; ++c) o[c][e] = (spec.kind[c] == 1 ? s1 : s2) * coef[c][e];
@@ -124,7 +129,6 @@ __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int d
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
                 const float x0 = o[c][e], x1 = o[c][e + 1];
-                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
                 const __half2 h = __floats2half2_rn(x0, x1);
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) layer0_jets_tc_kernel(JetSpec spec, int d
             if (three) *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
     }
-    if (!(amax < 65000.f)) atomicOr(status, kStatusRange);
+    if (!(smax * cmax < 65000.f)) atomicOr(status, kStatusRange);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,7 +18,9 @@ from .equations import JetSpec
 
 _state = threading.local()
 _test_backend = None          # tests only: CPU stand-in for the kernel (see _torch_jets.py)
-DEFAULT_PRECISION = os.environ.get("STPDE_PRECISION", "fp32")
+# "fp16x3": tcgen05 tensor cores with fp16 hi/lo split operands (fp32 parity, the default);
+# "fp32": FP32 FFMA on the CUDA cores (reference-exact arithmetic); "fp16": single-pass tensor cores (relaxed).
+DEFAULT_PRECISION = os.environ.get("STPDE_PRECISION", "fp16x3")
 
 
 def set_test_backend(fn) -> None:

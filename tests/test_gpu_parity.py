@@ -19,7 +19,7 @@ from tests.test_host_logic import bounds, build_model
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-PRECISIONS = [p for p in os.environ.get("STPDE_TEST_PRECISIONS", "fp32").split(",") if p]
+PRECISIONS = [p for p in os.environ.get("STPDE_TEST_PRECISIONS", "fp32,fp16x3,fp16").split(",") if p]
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +40,7 @@ def precision(request):
     TOL = TOLS[request.param]
     yield request.param
     TOL = 1e-5
-    jets.set_default_precision("fp32")
+    jets.set_default_precision("fp16x3")
 
 
 KINKED = ("relu", "leakyrelu")
