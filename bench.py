@@ -279,8 +279,20 @@ def main():
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     fpt = flops_per_point(NF, 3, CHANNELS, 4, KC)
     step_tflops = (value / world) * fpt / 1e12
+    passes = {"fp16x3": 3, "fp16": 1}.get(args.precision, 0)        # tensor-core MMAs per algorithmic product
+    n_launch = max(1, int(prof.get(dom, (0, 1))[1]))
+    traffic = None                                                  # DRAM bytes per launch from the committed ncu capture
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
+    if os.path.exists(ncu_path):
+        cap = json.load(open(ncu_path)).get(args.precision)
+        if cap:
+            rows_per_launch = NPTS * 8 / n_launch
+            traffic = cap["dram_bytes_per_launch"] * rows_per_launch / cap["rows_per_launch"]
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                "launches": n_launch, "avg_launch_ms": dom_ms / n_launch, "algorithmic_flops_per_launch": dom_flops / n_launch,
+                "tensor_passes": passes, "executed_tensor_tflops": achieved * passes if passes else None,
+                "executed_frac": achieved * passes / peaks["tflops"] if passes else None,
                 "launch_ms_total": dom_ms, "kernel_share_of_step": dom_ms / sum(kernel_ms.values()),
                 "step_achieved": step_tflops, "step_frac": step_tflops / peaks["tflops"],
                 "kernel_ms": kernel_ms,
