@@ -16,7 +16,7 @@ hdr, units, first = rows[0], rows[1], rows[2]
 def val(key):
     i = hdr.index(key)
     v = float(first[i].replace(",", ""))
-    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ms": 1e-3, "us": 1e-6, "s": 1, "%": 1}[units[i]]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1, "%": 1}[units[i]]
     return v * scale
 
 
