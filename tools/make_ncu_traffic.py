@@ -1,5 +1,5 @@
 """profiles/ncu_dominant_kernel.json: DRAM bytes per launch of the dominant kernel (hidden layer 1) from an
-`ncu --set full` capture of `tools/profile_step.py <precision> <npts>` run as a single chunk (rows = 8 * npts)."""
+`ncu --set full` capture of `tools/profile_step.py <precision> <npts>` with <npts> = points per chunk (rows = 8 * npts per launch)."""
 import csv
 import json
 import os
