@@ -149,6 +149,10 @@ struct LayerArgs {
     int passes;        // 3 = hi/lo split, 1 = single fp16 pass
     int dim, act, ncat, cat_off;
     float beta;
+    int n0;                // GEN mode: true width of layer 0 (= K of this layer before padding)
+    int vb_vec;            // GEN mode: Vb rows may be read with 16-byte loads
+    const float* wx0p;     // GEN mode: layer-0 coordinate columns, [kp_in][4] zero padded
+    const float* coef0;    // GEN mode: [KC][kp_in] per-feature jet coefficients * 2^4 (0 for pad features)
     const float* wscale;   // device: 2^-(sw_l + sa) for this layer
     const float* Wx;       // [n_feat][dim]
     const float* Vb;       // [nvert][ncat]
@@ -431,7 +435,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
         : "memory");
 }
 
-template <int KC>
+// GEN = true fuses layer 0 into this (layer 1) kernel: the activation operand tiles are not TMA-loaded from HBM
+// planes but GENERATED in shared memory by 8 generator warps from the closed-form layer-0 jets
+// (a_c = sigma^(k)(z0) * coef_c, z0 = Vb0[vertex] + W0x . x_rel), written in the SWIZZLE_128B K-major layout the
+// UMMA descriptors expect.  This removes layer 0's HBM round trip (412 GB / step at BASELINE config 2).
+template <int KC, bool GEN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -444,6 +452,9 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     constexpr uint32_t kWBytes = kTileF * kBlockK * 2;          // one W plane tile of this CTA (128 rows)
     constexpr uint32_t kABytes = (N / 2) * kBlockK * 2;         // this CTA's half of one activation plane tile
     constexpr uint32_t kTmemCols = 512;
+    constexpr int kEpiW = GEN ? 8 : kEpiWarps;                  // epilogue warps (rest of the CTA generates in GEN mode)
+    constexpr int kEpiPQ = kEpiW / 4;
+    constexpr int kGenWarps = 8, kGenPerStage = kGenWarps / 2;  // two sets of 4 warps alternate K blocks
     const bool three = args.passes == 3;
     const uint32_t stage_bytes = three ? 2 * kWBytes + 2 * kABytes : kWBytes + kABytes;
     const int n_stages = min((int)(kPairSmemBudget / stage_bytes), kPairMaxStages);
@@ -472,8 +483,9 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kPairMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps); }
+            // full: the leader's expect_tx arrival (+ one arrival per generator warp of BOTH CTAs in GEN mode)
+            for (int s = 0; s < kPairMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), GEN ? 1 + 2 * kGenPerStage : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiW); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -496,14 +508,17 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 const uint32_t base = smem_u32(smem + stage * stage_bytes);
                 const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
                 if (elect_one()) {
-                    if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * stage_bytes);   // bytes of BOTH CTAs
+                    const uint32_t tx = GEN ? (three ? 2 * kWBytes : kWBytes) : stage_bytes;    // TMA bytes per CTA
+                    if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * tx);            // bytes of BOTH CTAs
                     tma_load_2d_pair(base, &map_w_hi, kb * kBlockK, f0, fb);
                     if (three) tma_load_2d_pair(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
+                    if (!GEN) {
 #pragma unroll
-                    for (int rb = 0; rb < NRB / 2; ++rb) {
-                        tma_load_3d_pair(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
-                        if (three)
-                            tma_load_3d_pair(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        for (int rb = 0; rb < NRB / 2; ++rb) {
+                            tma_load_3d_pair(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                            if (three)
+                                tma_load_3d_pair(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        }
                     }
                 }
                 __syncwarp();
@@ -546,7 +561,104 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 }
             }
         }
-    } else {
+    } else if (GEN && warp >= 2 + kEpiW) {
+        // ===================== generator warps: layer-0 jets -> swizzled K-major operand tiles in smem =====================
+        const int gw = warp - (2 + kEpiW);
+        const int set = gw / kGenPerStage;                       // this warp serves K blocks of this parity
+        const int t128 = (gw % kGenPerStage) * 32 + lane;
+        constexpr int kItems = (NR / 2) * 8;                     // (local row, 16-byte chunk of 8 features)
+        constexpr int kPerThread = (kItems + 32 * kGenPerStage - 1) / (32 * kGenPerStage);
+        int stage = 0; uint32_t phase = 0;
+        uint32_t gcount = 0;
+        for (int t = pair_id; t < n_tiles; t += n_pairs) {
+            const int r0 = (t / n_ftiles) * NR + (int)rank * (NR / 2);
+            // per-item row data is the same for every K block of the tile
+            int vrow[kPerThread];
+            float xr[kPerThread][kMaxDim];
+            bool rok[kPerThread];
+#pragma unroll
+            for (int q = 0; q < kPerThread; ++q) {
+                const int item = t128 + q * 32 * kGenPerStage;
+                const int r = r0 + (item >> 3);
+                rok[q] = item < kItems && r < args.rows;
+                const int rc = min(r, args.rows - 1);
+                vrow[q] = __ldg(args.vtx + rc);
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k) xr[q][k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
+            }
+            for (int kb = 0; kb < kb_count; ++kb, ++gcount) {
+                if ((gcount & 1u) == (uint32_t)set) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                    uint8_t* a_tile = smem + stage * stage_bytes + (three ? 2 * kWBytes : kWBytes);
+#pragma unroll
+                    for (int q = 0; q < kPerThread; ++q) {
+                        const int item = t128 + q * 32 * kGenPerStage;
+                        if (item >= kItems) continue;
+                        const int rl = item >> 3, j = item & 7;
+                        const int f0g = kb * kBlockK + j * 8;
+                        float o[KC][8];
+                        if (rok[q]) {
+                            // tables are padded to the K block: features >= n0 have zero coefficients
+                            const float4* vb4 = reinterpret_cast<const float4*>(args.Vb + (int64_t)vrow[q] * args.ncat + f0g);
+                            const float4* wx4 = reinterpret_cast<const float4*>(args.wx0p) + f0g;
+                            float vb[8];
+                            if (args.vb_vec) {
+                                const float4 a = __ldg(vb4), b = __ldg(vb4 + 1);
+                                vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w; vb[4] = b.x; vb[5] = b.y; vb[6] = b.z; vb[7] = b.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vb[e] = (f0g + e < args.n0) ? __ldg(args.Vb + (int64_t)vrow[q] * args.ncat + f0g + e) : 0.f;
+                            }
+                            float sg[3][8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float4 w = __ldg(wx4 + e);
+                                float z = vb[e];
+                                z = fmaf(w.x, xr[q][0], z); z = fmaf(w.y, xr[q][1], z);
+                                z = fmaf(w.z, xr[q][2], z); z = fmaf(w.w, xr[q][3], z);
+                                act_jet_fast(args.act, args.beta, z, sg[0][e], sg[1][e], sg[2][e]);
+                            }
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) {
+                                const float4* cf4 = reinterpret_cast<const float4*>(args.coef0 + (int64_t)c * args.kp_in + f0g);
+                                const float4 a = __ldg(cf4), b = __ldg(cf4 + 1);
+                                const float cf[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    o[c][e] = (spec.kind[c] == 0 ? sg[0][e] : spec.kind[c] == 1 ? sg[1][e] : sg[2][e]) * cf[e];
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < KC; ++c)
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) o[c][e] = 0.f;
+                        }
+                        const int rbl = rl >> 3, i = rl & 7;
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) {
+                            uint32_t ph[4], pl[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const __half2 h = __floats2half2_rn(o[c][e], o[c][e + 1]);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(o[c][e] - hf.x, o[c][e + 1] - hf.y);
+                                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                            const uint32_t row = rbl * (8 * KC) + c * 8 + i;                 // row of the operand tile
+                            uint8_t* dst = a_tile + row * 128 + ((j ^ i) << 4);               // SWIZZLE_128B: chunk ^ (row % 8)
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            if (three) *reinterpret_cast<uint4*>(dst + kABytes) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&full_bar[stage]), 0));
+                }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 2 + kEpiW) {
         // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
@@ -591,12 +703,12 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
             float amax = 0.f;
 #pragma unroll 1
-            for (int rb = sub; rb < NRB; rb += kEpiPerQuarter) {
+            for (int rb = sub; rb < NRB; rb += kEpiPQ) {
                 uint32_t v[KC][8];
 #pragma unroll
                 for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
                 float zs_next[8];
-                if (rb + kEpiPerQuarter < NRB) load_skip(r0 + (rb + kEpiPerQuarter) * 8, g, wx, zs_next);
+                if (rb + kEpiPQ < NRB) load_skip(r0 + (rb + kEpiPQ) * 8, g, wx, zs_next);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

@@ -51,6 +51,25 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
     }
 }
 
+// Tables for the fused layer-0 generator: wx0p [kp][4] (zero padded) and coef [KC][kp] with
+// coef[0] = 2^4, first order = W0x[:, dir] * 2^4, second order = W0x[:, a] * W0x[:, b] * 2^4 (0 for pad features)
+__global__ void gen_tables_kernel(JetSpec spec, int dim, int n0, int kp, const float* __restrict__ Wx0,
+                                  float* __restrict__ wx0p, float* __restrict__ coef) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= kp) return;
+    float wx[kMaxDim] = {0.f, 0.f, 0.f, 0.f};
+    const bool ok = f < n0;
+    for (int k = 0; k < dim; ++k) wx[k] = ok ? Wx0[f * dim + k] : 0.f;
+    for (int k = 0; k < kMaxDim; ++k) wx0p[f * 4 + k] = wx[k];
+    const float sc = ok ? (float)(1 << tc::kActScaleLog2) : 0.f;
+    for (int c = 0; c < spec.kc; ++c) {
+        float v = sc;
+        if (spec.kind[c] == 1) v *= wx[spec.dir[c]];
+        if (spec.kind[c] == 2) v *= wx[spec.dir[spec.pa[c]]] * wx[spec.dir[spec.pb[c]]];
+        coef[(int64_t)c * kp + f] = v;
+    }
+}
+
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
 // One thread = 8 consecutive features of one row: 16-byte stores, coalesced 512 B per warp and plane.
 template <int KC>
@@ -148,6 +167,7 @@ __global__ void __launch_bounds__(256, 2) layer0_jets_tc_kernel(JetSpec spec, in
 // ---------------------------------------------------------------------------------------------
 size_t tc_fixed_bytes(int n_layers, const int* widths) {
     size_t off = 1024;  // wscale + absmax
+    off += align_up((size_t)round_up(widths[0], 64) * (4 + kMaxComp) * sizeof(float), 1024);  // generator tables
     for (int l = 1; l <= n_layers - 2; ++l) {
         size_t plane = (size_t)round_up(widths[l], 128) * round_up(widths[l - 1], 64) * sizeof(__half);
         off += 2 * align_up(plane, 1024);
@@ -225,6 +245,11 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.status = status;
     const char* pair_env = getenv("STPDE_TC_PAIR");
     tc.use_pair = pair_env ? atoi(pair_env) : 1;
+    // Fusing layer 0 into layer 1's operand producer (generator warps) is functional but measured SLOWER on B200
+    // (905 ms vs 435 + 122 ms at BASELINE config 2: the generator needs ~2000 issue slots per K block and the
+    // 4 feature-tile passes recompute it 4 times), so it is opt-in: STPDE_TC_FUSE0=1.
+    const char* fuse_env = getenv("STPDE_TC_FUSE0");
+    tc.fuse0 = fuse_env ? atoi(fuse_env) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -233,6 +258,9 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.absmax = (unsigned*)(fixed_ws + 512);
     cudaMemsetAsync(tc.absmax, 0, 256, st);
     size_t off = 1024;
+    tc.wx0p = (float*)(fixed_ws + off);
+    tc.coef0 = tc.wx0p + (size_t)round_up(widths[0], 64) * 4;
+    off += align_up((size_t)round_up(widths[0], 64) * (4 + kMaxComp) * sizeof(float), 1024);
     int me, mo;
     plane_lds(n_layers, widths, me, mo);
     const size_t plane_even = (size_t)kc * rows * me * sizeof(__half), plane_odd = (size_t)kc * rows * mo * sizeof(__half);
@@ -294,21 +322,21 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     return STPDE_OK;
 }
 
-template <int KC>
+template <int KC, bool GEN>
 static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
                              cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
         configured = true;
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = tc.num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    tc::tc_layer_pair_kernel<KC, GEN><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -338,7 +366,8 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
                  const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
                  int np_last, cudaStream_t st) {
     if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_prepare");
-    {
+    const bool fuse0 = tc.use_pair && tc.fuse0 && tc.layer[1].n_feat >= 2 * tc::kTileF;
+    if (!fuse0) {
         ProfScope ps(kSlotLayer0, st);
         STPDE_TC_DISPATCH_KC(spec.kc, launch_layer0_tc<KC>(tc, spec, dim, act, beta, cb, tc.n0,
                                                            (const float*)(ws + off_wx[0]), Vb, ncat, st));
@@ -370,8 +399,19 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         a.status = tc.status;
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
-        if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
-            STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer_pair<KC>(tc, L, spec, a, st));
+        a.n0 = tc.n0;
+        a.wx0p = tc.wx0p;
+        a.coef0 = tc.coef0;
+        a.vb_vec = (ncat % 4 == 0) && (tc.n0 % 64 == 0);
+        if (l == 1 && fuse0 && !tc.tables_ready) {
+            gen_tables_kernel<<<(L.kp_in + 127) / 128, 128, 0, st>>>(spec, dim, tc.n0, L.kp_in,
+                                                                      (const float*)(ws + off_wx[0]), tc.wx0p, tc.coef0);
+            tc.tables_ready = 1;
+        }
+        if (l == 1 && fuse0) {
+            STPDE_TC_DISPATCH_KC(spec.kc, (rc = launch_layer_pair<KC, true>(tc, L, spec, a, st)));
+        } else if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
+            STPDE_TC_DISPATCH_KC(spec.kc, (rc = launch_layer_pair<KC, false>(tc, L, spec, a, st)));
         } else {
             STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer<KC>(tc, L, spec, a, st));
         }

@@ -16,7 +16,8 @@ struct TcLayerPlan {
 };
 
 struct TcContext {
-    int n_layers, kc, rows, passes, num_sms, use_pair;
+    int n_layers, kc, rows, passes, num_sms, use_pair, fuse0, tables_ready;
+    float *wx0p, *coef0;              // fused layer-0 generator tables
     TcLayerPlan layer[kMaxLayers];     // hidden layers 1..n_layers-2
     __half* act[2][2];                 // [buffer parity][hi/lo] planes [KC][rows][ld]
     int ld0, n0;                       // row stride / true width of layer 0's output planes
