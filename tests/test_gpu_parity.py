@@ -332,3 +332,50 @@ def test_full_size_properties(dev, precision):
     for i, a in enumerate((0, 1, 2)):
         assert rel_linf(jt[i], yj.g[a]) < TOL
     assert rel_linf(jt[3], yj.h[1][1]) < TOL and rel_linf(jt[4], yj.h[2][2]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# wide decoders (CTA-pair tensor-core kernel: layers >= 256 features) x jet specifications x dimensions
+# ---------------------------------------------------------------------------------------------
+def _oracle_planes(yj, spec):
+    return [yj.g[a] for a in spec.first] + [yj.h[a][b] for a, b in spec.second]
+
+
+WIDE_CASES = [
+    # (dim, grid, c, o, nf, act, first, second)
+    (3, (3, 4, 5), 16, 4, 32, "softplus", (), ()),                                             # values only, K = 1
+    (3, (3, 4, 5), 16, 4, 32, "tanh", (0, 1, 2), ()),                                          # gradient, K = 4
+    (3, (4, 16, 16), 32, 4, 32, "softplus", (0, 1, 2), ((1, 1), (2, 2))),                      # RB2 shape, K = 6
+    (3, (3, 4, 5), 16, 4, 64, "swish", (0, 1, 2), ((0, 0), (1, 1), (2, 2))),                   # steady NS Laplacians, K = 7
+    (4, (3, 3, 4, 3), 8, 4, 32, "elu", (0, 1, 2, 3), ((0, 0), (1, 1), (2, 2))),                # 4-d NS (config 4), K = 8
+    (3, (3, 4, 5), 16, 3, 32, "tanh", (0, 1, 2), tuple((a, b) for a in range(3) for b in range(a, 3))),  # Hessian, K = 10
+    (2, (5, 6), 12, 2, 32, "softplus", (0, 1), ((0, 0), (0, 1), (1, 1))),                      # d = 2, K = 6
+    (1, (7,), 8, 2, 32, "swish", (0,), ((0, 0),)),                                             # d = 1, K = 3
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=[f"d{c[0]}_nf{c[4]}_{c[5]}_K{1 + len(c[6]) + len(c[7])}" for c in WIDE_CASES])
+def test_wide_decoder_jets_vs_oracle(case, dev, precision):
+    dim, gshape, c, o, nf, act, first, second = case
+    torch.manual_seed(100 + dim * 7 + nf)
+    model = sp.ImNet(dim=dim, in_features=c, out_features=o, nf=nf, activation=sp.NONLINEARITIES[act]).to(dev)
+    if act == "swish":
+        with torch.no_grad():
+            model.activ.beta.fill_(0.8)
+    grid = torch.randn(2, *gshape, c, device=dev) * 0.6
+    q = torch.rand(2, 300, dim, device=dev)            # 600 points: ragged last tile for every K
+    spec = JetSpec(tuple(first), tuple(second))
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), act, model.activ.beta if act == "swish" else None,
+                               spec=spec)
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    beta = float(model.activ.beta.detach()) if act == "swish" else 1.0
+    yj = jo.query_jet(grid.cpu().numpy(), q.cpu().numpy(), 0., 1., Ws, bs, act, beta)
+    assert rel_linf(y.cpu().numpy(), yj.v) < TOL
+    # elu has a discontinuous second derivative at 0 (relu-like kink one order up): isolated points whose
+    # pre-activation is within rounding of 0 flip sigma'' in any fp32 implementation -> quantile metric
+    metric = rel_err_quantile if act in ("elu",) + KINKED else rel_linf
+    if spec.n_jet:
+        for plane, ref in zip(jt.cpu().numpy(), _oracle_planes(yj, spec)):
+            assert metric(plane, ref) < TOL
