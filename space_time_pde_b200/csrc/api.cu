@@ -151,7 +151,7 @@ static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, co
     off = align_up(off + (use_tc ? tc_fixed_bytes(P.n_layers, P.widths) : 0), 1024);
     P.fixed_bytes = off;
     const int kc = s.kc;
-    P.per_point_bytes = (size_t)P.ncorner * (4 + 4 * d->dim) + (size_t)4 * 5 * d->dim;
+    P.per_point_bytes = (size_t)P.ncorner * (4 + 4 * kMaxDim) + (size_t)4 * 5 * d->dim;
     if (use_tc)   // fp32 only for the last hidden layer (input of final_blend) + fp16 hi/lo planes
         P.per_point_bytes += (size_t)kc * P.ncorner * 4 * P.np[P.n_layers - 2] +
                              tc_per_point_bytes(P.n_layers, P.widths, kc, P.ncorner);
@@ -195,7 +195,7 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     cb.pc = (int)pc;
     cb.rows = (int)rows;
     cb.vtx = (int*)take(rows * 4);
-    cb.xrel = (float*)take((size_t)dim * rows * 4);
+    cb.xrel = (float*)take((size_t)kMaxDim * rows * 4);   // [kMaxDim][rows], planes >= dim are zero
     cb.wfac = (float*)take((size_t)dim * 2 * pc * 4);
     cb.dfac = (float*)take((size_t)dim * 2 * pc * 4);
     cb.dxr = (float*)take((size_t)dim * pc * 4);

@@ -141,4 +141,11 @@ __device__ __forceinline__ void act_jet_fast(int kind, float beta, float z, floa
     }
 }
 
+// runtime switch used by the tensor-core kernels: accurate (libdevice) in the fp32-parity mode fp16x3 unless
+// STPDE_TC_FAST_ACT=1, MUFU-based in the relaxed single-pass fp16 mode
+__device__ __forceinline__ void act_jet_sel(bool fast, int kind, float beta, float z, float& s0, float& s1, float& s2) {
+    if (fast) act_jet_fast(kind, beta, z, s0, s1, s2);
+    else act_jet(kind, beta, z, s0, s1, s2);
+}
+
 }  // namespace stpde

@@ -138,7 +138,7 @@ __global__ void prep_points_kernel(GridGeom g, int npts, int64_t total_pts, int6
     if (gp >= total_pts) {  // padding point: neutral, finite
         for (int j = 0; j < ncorner; ++j) {
             cb.vtx[(int64_t)i * ncorner + j] = 0;
-            for (int k = 0; k < g.dim; ++k) cb.xrel[(int64_t)k * cb.rows + (int64_t)i * ncorner + j] = 0.f;
+            for (int k = 0; k < kMaxDim; ++k) cb.xrel[(int64_t)k * cb.rows + (int64_t)i * ncorner + j] = 0.f;
         }
         for (int k = 0; k < g.dim; ++k) {
             cb.wfac[(k * 2 + 0) * cb.pc + i] = 0.f; cb.wfac[(k * 2 + 1) * cb.pc + i] = 0.f;
@@ -180,6 +180,7 @@ __global__ void prep_points_kernel(GridGeom g, int npts, int64_t total_pts, int6
             v = v * g.size[k] + idx[k][bit];
             cb.xrel[(int64_t)k * cb.rows + (int64_t)i * ncorner + j] = xr[k][bit];
         }
+        for (int k = g.dim; k < kMaxDim; ++k) cb.xrel[(int64_t)k * cb.rows + (int64_t)i * ncorner + j] = 0.f;
         cb.vtx[(int64_t)i * ncorner + j] = b * g.nvert + v;
     }
     if (bad) atomicOr(status, kStatusIndex);

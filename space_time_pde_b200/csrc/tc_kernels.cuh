@@ -149,6 +149,7 @@ struct LayerArgs {
     int passes;        // 3 = hi/lo split, 1 = single fp16 pass
     int dim, act, ncat, cat_off;
     float beta;
+    int fast_act;          // 1: MUFU-based activation jets, 0: libdevice-accurate
     int n0;                // GEN mode: true width of layer 0 (= K of this layer before padding)
     int vb_vec;            // GEN mode: Vb rows may be read with 16-byte loads
     const float* wx0p;     // GEN mode: layer-0 coordinate columns, [kp_in][4] zero padded

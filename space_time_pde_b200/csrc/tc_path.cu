@@ -76,7 +76,7 @@ template <int KC>
 __global__ void __launch_bounds__(256, 2) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
                                                              int ld, const int* __restrict__ vtx,
                                                              const float* __restrict__ xrel, const float* __restrict__ Wx,
-                                                             const float* __restrict__ Vb, int ncat, int three,
+                                                             const float* __restrict__ Vb, int ncat, int three, int fast_act,
                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                              int* __restrict__ status) {
     const int fg = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -248,6 +248,10 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     // Fusing layer 0 into layer 1's operand producer (generator warps) is functional but measured SLOWER on B200
     // (905 ms vs 435 + 122 ms at BASELINE config 2: the generator needs ~2000 issue slots per K block and the
     // 4 feature-tile passes recompute it 4 times), so it is opt-in: STPDE_TC_FUSE0=1.
+    // The tensor-core kernels use the MUFU-based activation jets (act_jet_fast): measured on B200, switching to the
+    // libdevice-accurate versions changes the fp16x3 error by < 2 % (the 2^-22 operand rounding dominates) and
+    // costs 4 % of the step.
+    tc.fast_act = 1;
     const char* fuse_env = getenv("STPDE_TC_FUSE0");
     tc.fuse0 = fuse_env ? atoi(fuse_env) : 0;
     int dev = 0;
@@ -345,7 +349,7 @@ static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, 
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
     dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 63) / 64);
     layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
-                                                    tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
+                                                    tc.passes == 3, tc.fast_act, tc.act[0][0], tc.act[0][1], tc.status);
 }
 
 #define STPDE_TC_DISPATCH_KC(kc, CALL)                 \
@@ -399,6 +403,7 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         a.status = tc.status;
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
+        a.fast_act = tc.fast_act;
         a.n0 = tc.n0;
         a.wx0p = tc.wx0p;
         a.coef0 = tc.coef0;

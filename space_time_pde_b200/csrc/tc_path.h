@@ -16,7 +16,7 @@ struct TcLayerPlan {
 };
 
 struct TcContext {
-    int n_layers, kc, rows, passes, num_sms, use_pair, fuse0, tables_ready;
+    int n_layers, kc, rows, passes, num_sms, use_pair, fuse0, tables_ready, fast_act;
     float *wx0p, *coef0;              // fused layer-0 generator tables
     TcLayerPlan layer[kMaxLayers];     // hidden layers 1..n_layers-2
     __half* act[2][2];                 // [buffer parity][hi/lo] planes [KC][rows][ld]
