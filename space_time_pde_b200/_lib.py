@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libstpde.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "simt_kernels.cu", "tc_path.cu", "profile.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "tc_path.cu", "tc_layers_a.cu", "tc_layers_b.cu", "tc_layers_c.cu", "profile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -64,14 +64,31 @@ def sources_newer_than_lib() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into libstpde.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into libstpde.so (nvcc cross-compiles without a GPU).
+
+    Translation units are compiled in parallel (one nvcc per .cu into build/*.o) and linked once."""
     if not force and not sources_newer_than_lib():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-lcuda"]
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = ["nvcc"] + flags + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcuda"]
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, cwd=CSRC)
+        print(" ".join(link), flush=True)
+    subprocess.run(link, check=True, cwd=CSRC)
     return LIB_PATH
 
 

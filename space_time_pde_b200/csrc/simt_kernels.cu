@@ -430,6 +430,58 @@ __global__ void __launch_bounds__(256) layer_gemm_kernel(JetSpec spec, int dim, 
     }
 }
 
+// Last linear layer for the nvec = KC * 128 (component, local row) vectors of a CTA.  Each warp takes batches of
+// RB = 32 / OP vectors; a lane accumulates the OP partial dot products over its float4 slices of K (coalesced
+// 512 B loads), then a transpose-reduce over the warp (31 shuffles for 32 values) leaves lane L with the finished
+// sum of (vector L / OP, output L % OP).
+template <int OP>
+__device__ __forceinline__ void final_gemv(int nvec, int row0, int rows, int Kp, int O, const float* __restrict__ actIn,
+                                           const float* Ws, const float* __restrict__ blast, float* outc) {
+    constexpr int RB = 32 / OP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b0 = warp * RB; b0 < nvec; b0 += 8 * RB) {
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const int vec = b0 + j;
+            const int c = vec / 128, lr = vec % 128;
+            const int r = row0 + lr;
+            if (vec < nvec && r < rows) {
+                const float4* a4 = reinterpret_cast<const float4*>(actIn + ((int64_t)c * rows + r) * Kp);
+                for (int q4 = lane; q4 < Kp / 4; q4 += 32) {
+                    const float4 a = __ldg(a4 + q4);
+#pragma unroll
+                    for (int o = 0; o < OP; ++o) {
+                        if (o < O) {
+                            const float4 w = *reinterpret_cast<const float4*>(Ws + o * Kp + q4 * 4);
+                            v[j * OP + o] += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < sft) {
+                    const bool up = (lane & sft) != 0;
+                    const float send = up ? v[j] : v[j + sft];
+                    const float keep = up ? v[j + sft] : v[j];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                }
+            }
+        }
+        const int vec = b0 + lane / OP, o = lane % OP;
+        if (vec < nvec && o < O) {
+            const int c = vec / 128, lr = vec % 128;
+            outc[(c * 128 + lr) * O + o] = v[0] + (c == 0 ? blast[o] : 0.f);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // final_blend: last linear layer (no activation) + blend over the 2^d corners with product rule.
 // One CTA = 128 (point, corner) rows.
@@ -449,120 +501,64 @@ __global__ void __launch_bounds__(256) final_blend_kernel(JetSpec spec, int dim,
     const int row0 = blockIdx.x * 128;
     for (int e = threadIdx.x; e < O * Kp; e += blockDim.x) Ws[e] = Wlast[e];
     __syncthreads();
-    // last linear layer: stage a [128 rows x 128 k] tile in smem (coalesced 512 B row segments), then two
-    // threads per row accumulate the O dot products (row stride 129 floats -> conflict-free column walks)
-    float* tile = outc + KC * 128 * O;   // [128][129]
-    float* part = tile + 128 * 129;      // [128][kMaxOut] partial sums of the upper k half
-    const int lr = threadIdx.x & 127, kh = threadIdx.x >> 7;
-    for (int c = 0; c < KC; ++c) {
-        float acc[kMaxOut];
-#pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
-        for (int k0 = 0; k0 < Kp; k0 += 128) {
-            const int kw = min(128, Kp - k0);
-            __syncthreads();
-            for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {       // 128 rows x 32 float4
-                const int rr = e >> 5, q4 = (e & 31) * 4;
-                const int r = row0 + rr;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows && q4 < kw) v = *reinterpret_cast<const float4*>(actIn + ((int64_t)c * rows + r) * Kp + k0 + q4);
-                float* dst = tile + rr * 129 + q4;
-                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-            }
-            __syncthreads();
-            const int kbeg = kh * 64, kend = min(kbeg + 64, kw);
-            for (int k = kbeg; k < kend; ++k) {
-                const float av = tile[lr * 129 + k];
-#pragma unroll
-                for (int o = 0; o < kMaxOut; ++o)
-                    if (o < O) acc[o] = fmaf(av, Ws[o * Kp + k0 + k], acc[o]);
-            }
-        }
-        if (kh == 1) {
-#pragma unroll
-            for (int o = 0; o < kMaxOut; ++o) part[lr * kMaxOut + o] = acc[o];
-        }
-        __syncthreads();
-        if (kh == 0) {
-#pragma unroll
-            for (int o = 0; o < kMaxOut; ++o)
-                if (o < O) outc[(c * 128 + lr) * O + o] = acc[o] + part[lr * kMaxOut + o] + (c == 0 ? blast[o] : 0.f);
-        }
+    switch (O <= 1 ? 1 : O <= 2 ? 2 : O <= 4 ? 4 : 8) {
+        case 1: final_gemv<1>(KC * 128, row0, rows, Kp, O, actIn, Ws, blast, outc); break;
+        case 2: final_gemv<2>(KC * 128, row0, rows, Kp, O, actIn, Ws, blast, outc); break;
+        case 4: final_gemv<4>(KC * 128, row0, rows, Kp, O, actIn, Ws, blast, outc); break;
+        default: final_gemv<8>(KC * 128, row0, rows, Kp, O, actIn, Ws, blast, outc); break;
     }
     __syncthreads();
-    // blend: thread per (point, output)
+    // blend over the 2^d corners with the product rule: one thread per (point, output, jet component)
     const int pts_per_cta = 128 / ncorner;
-    for (int e = threadIdx.x; e < pts_per_cta * O; e += blockDim.x) {
-        const int lp = e / O, o = e % O;
+    for (int e = threadIdx.x; e < pts_per_cta * O * KC; e += blockDim.x) {
+        const int c = e % KC, o = (e / KC) % O, lp = e / (KC * O);
         const int i = row0 / ncorner + lp;  // point index within the chunk
         const int64_t gp = p0 + i;
         if (i >= pc || gp >= total_pts) continue;
         float f[kMaxDim][2], df[kMaxDim][2], dx[kMaxDim];
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) {
+            f[k][0] = f[k][1] = 1.f; df[k][0] = df[k][1] = 0.f; dx[k] = 0.f;
             if (k < dim) {
                 f[k][0] = cb.wfac[(k * 2 + 0) * cb.pc + i]; f[k][1] = cb.wfac[(k * 2 + 1) * cb.pc + i];
                 df[k][0] = cb.dfac[(k * 2 + 0) * cb.pc + i]; df[k][1] = cb.dfac[(k * 2 + 1) * cb.pc + i];
                 dx[k] = cb.dxr[k * cb.pc + i];
             }
         }
-        float res[KC];
+        const int kind = spec.kind[c];
+        const int ca = kind == 2 ? spec.pa[c] : c, cbi = kind == 2 ? spec.pb[c] : c;   // parent components
+        const int a = kind == 1 ? spec.dir[c] : spec.dir[ca], b = spec.dir[cbi];      // directions
+        float dxa = 0.f, dxb = 0.f;
 #pragma unroll
-        for (int c = 0; c < KC; ++c) res[c] = 0.f;
+        for (int k = 0; k < kMaxDim; ++k) { if (k == a) dxa = dx[k]; if (k == b) dxb = dx[k]; }
+        float res = 0.f;
         for (int j = 0; j < ncorner; ++j) {
             const int lr = lp * ncorner + j;
-            float oc[KC];
-#pragma unroll
-            for (int c = 0; c < KC; ++c) oc[c] = outc[(c * 128 + lr) * O + o];
-            int bit[kMaxDim];
-            float w = 1.f;
+            const float o0 = outc[lr * O + o];                       // value component of this corner
+            const float oc = outc[(c * 128 + lr) * O + o];
+            float w = 1.f, wa = 1.f, wb = 1.f, wab = 1.f;            // weight and its derivatives along a, b, (a,b)
 #pragma unroll
             for (int k = 0; k < kMaxDim; ++k) {
                 if (k < dim) {
-                    bit[k] = (j >> (dim - 1 - k)) & 1;
-                    w = (k == 0) ? f[k][bit[k]] : __fmul_rn(w, f[k][bit[k]]);  // torch.prod order
+                    const int bit = (j >> (dim - 1 - k)) & 1;
+                    const float fk = f[k][bit], dk = df[k][bit];
+                    w = (k == 0) ? fk : __fmul_rn(w, fk);            // torch.prod order
+                    wa *= (k == a) ? dk : fk;
+                    wb *= (k == b) ? dk : fk;
+                    wab *= (k == a || k == b) ? dk : fk;
                 }
             }
-            // derivative of the blend weight along direction a (and a,b)
-            auto wd1 = [&](int a) {
-                float v = 1.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < dim) v *= (k == a) ? df[k][bit[k]] : f[k][bit[k]];
-                return v;
-            };
-            auto wd2 = [&](int a, int b) {
-                if (a == b) return 0.f;
-                float v = 1.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < dim) v *= (k == a || k == b) ? df[k][bit[k]] : f[k][bit[k]];
-                return v;
-            };
-            res[0] = __fadd_rn(res[0], __fmul_rn(oc[0], w));  // torch.sum(output * weights) in corner order
-#pragma unroll
-            for (int c = 1; c < KC; ++c) {
-                if (c <= spec.n_first) {
-                    const int a = spec.first_dirs[c - 1];
-                    res[c] += wd1(a) * oc[0] + w * dx[a] * oc[c];
-                } else {
-                    const int s = c - 1 - spec.n_first;
-                    const int ca = spec.sec_a[s], cbi = spec.sec_b[s];
-                    const int a = spec.first_dirs[ca - 1], b = spec.first_dirs[cbi - 1];
-                    float oa = 0.f, ob = 0.f;
-#pragma unroll
-                    for (int cc = 1; cc < KC; ++cc) {
-                        if (cc == ca) oa = oc[cc];
-                        if (cc == cbi) ob = oc[cc];
-                    }
-                    res[c] += wd2(a, b) * oc[0] + wd1(a) * dx[b] * ob + wd1(b) * dx[a] * oa +
-                              w * dx[a] * dx[b] * oc[c];
-                }
+            if (kind == 0) {
+                res = __fadd_rn(res, __fmul_rn(o0, w));              // torch.sum(output * weights) in corner order
+            } else if (kind == 1) {
+                res += wa * o0 + w * dxa * oc;
+            } else {
+                const float oa = outc[(ca * 128 + lr) * O + o], ob = outc[(cbi * 128 + lr) * O + o];
+                res += (a == b ? 0.f : wab) * o0 + wa * dxb * ob + wb * dxa * oa + w * dxa * dxb * oc;
             }
         }
-        y[gp * O + o] = res[0];
-#pragma unroll
-        for (int c = 1; c < KC; ++c) jets[((int64_t)(c - 1) * total_pts + gp) * O + o] = res[c];
+        if (c == 0) y[gp * O + o] = res;
+        else jets[((int64_t)(c - 1) * total_pts + gp) * O + o] = res;
     }
 }
 
@@ -672,7 +668,7 @@ template <int KC>
 static void launch_final_t(const JetSpec& spec, int dim, int rows, int pc, int64_t total_pts, int64_t p0, int Kp,
                            int O, const float* actIn, const float* Wlast, const float* blast,
                            const ChunkBuffers& cb, float* y, float* jets, cudaStream_t st) {
-    size_t smem = (size_t)(O * Kp + KC * 128 * O + 128 * 129 + 128 * kMaxOut) * sizeof(float);
+    size_t smem = (size_t)(O * Kp + KC * 128 * O) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(final_blend_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -1,0 +1,67 @@
+// Launch wrappers of the tensor-core layer kernels.  The kernel templates are instantiated for K = 1..10 jet
+// components in three separate translation units (tc_layers_a/b/c.cu) so that the build parallelises.
+#pragma once
+#include "tc_kernels.cuh"
+#include "tc_path.h"
+
+namespace stpde {
+
+int tc_fail(int code, const char* msg);
+int tc_launch_layer(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+int tc_launch_layer_pair(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+int tc_launch_layer_pair_gen(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+
+#define STPDE_TC_DISPATCH_KC(kc, CALL)                 \
+    switch (kc) {                                      \
+        case 1: { constexpr int KC = 1; CALL; } break; \
+        case 2: { constexpr int KC = 2; CALL; } break; \
+        case 3: { constexpr int KC = 3; CALL; } break; \
+        case 4: { constexpr int KC = 4; CALL; } break; \
+        case 5: { constexpr int KC = 5; CALL; } break; \
+        case 6: { constexpr int KC = 6; CALL; } break; \
+        case 7: { constexpr int KC = 7; CALL; } break; \
+        case 8: { constexpr int KC = 8; CALL; } break; \
+        case 9: { constexpr int KC = 9; CALL; } break; \
+        default: { constexpr int KC = 10; CALL; } break; \
+    }
+
+#ifdef STPDE_TC_LAUNCH_IMPL
+template <int KC>
+static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
+                        cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    constexpr int N = KC * NR;
+    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
+        configured = true;
+    }
+    const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
+    const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
+    tc::tc_layer_kernel<KC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    return STPDE_OK;
+}
+
+template <int KC, bool GEN>
+static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
+                             cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
+        configured = true;
+    }
+    const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
+    const int max_pairs = tc.num_sms / 2;
+    const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
+    tc::tc_layer_pair_kernel<KC, GEN><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    return STPDE_OK;
+}
+
+#endif  // STPDE_TC_LAUNCH_IMPL
+
+}  // namespace stpde

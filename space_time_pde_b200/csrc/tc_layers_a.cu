@@ -1,0 +1,11 @@
+// Single-CTA tensor-core layer kernel (M = 128), instantiations K = 1..10.
+#define STPDE_TC_LAUNCH_IMPL
+#include "tc_launch.cuh"
+
+namespace stpde {
+int tc_launch_layer(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
+    int rc = STPDE_OK;
+    STPDE_TC_DISPATCH_KC(kc, rc = launch_layer<KC>(tc, L, spec, a, st));
+    return rc;
+}
+}  // namespace stpde

@@ -7,12 +7,13 @@
 
 #include "profile.h"
 #include "tc_kernels.cuh"
+#include "tc_launch.cuh"
 
 namespace stpde {
 
 static thread_local char g_tc_err[256] = "";
 const char* tc_last_error() { return g_tc_err; }
-static int tc_fail(int code, const char* msg) { snprintf(g_tc_err, sizeof(g_tc_err), "%s", msg); return code; }
+int tc_fail(int code, const char* msg) { snprintf(g_tc_err, sizeof(g_tc_err), "%s", msg); return code; }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -309,62 +310,12 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
 }
 
 template <int KC>
-static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
-                        cudaStream_t st) {
-    constexpr int NR = tc::rows_per_tile(KC);
-    constexpr int N = KC * NR;
-    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
-        configured = true;
-    }
-    const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
-    const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
-    tc::tc_layer_kernel<KC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
-    return STPDE_OK;
-}
-
-template <int KC, bool GEN>
-static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
-                             cudaStream_t st) {
-    constexpr int NR = tc::rows_per_tile(KC);
-    const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
-        configured = true;
-    }
-    const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
-    const int max_pairs = tc.num_sms / 2;
-    const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, GEN><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
-    return STPDE_OK;
-}
-
-template <int KC>
 static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
     dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 63) / 64);
     layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
                                                     tc.passes == 3, tc.fast_act, tc.act[0][0], tc.act[0][1], tc.status);
 }
-
-#define STPDE_TC_DISPATCH_KC(kc, CALL)                 \
-    switch (kc) {                                      \
-        case 1: { constexpr int KC = 1; CALL; } break; \
-        case 2: { constexpr int KC = 2; CALL; } break; \
-        case 3: { constexpr int KC = 3; CALL; } break; \
-        case 4: { constexpr int KC = 4; CALL; } break; \
-        case 5: { constexpr int KC = 5; CALL; } break; \
-        case 6: { constexpr int KC = 6; CALL; } break; \
-        case 7: { constexpr int KC = 7; CALL; } break; \
-        case 8: { constexpr int KC = 8; CALL; } break; \
-        case 9: { constexpr int KC = 9; CALL; } break; \
-        default: { constexpr int KC = 10; CALL; } break; \
-    }
 
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                  const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
@@ -414,11 +365,11 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
             tc.tables_ready = 1;
         }
         if (l == 1 && fuse0) {
-            STPDE_TC_DISPATCH_KC(spec.kc, (rc = launch_layer_pair<KC, true>(tc, L, spec, a, st)));
+            rc = tc_launch_layer_pair_gen(spec.kc, tc, L, spec, a, st);
         } else if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
-            STPDE_TC_DISPATCH_KC(spec.kc, (rc = launch_layer_pair<KC, false>(tc, L, spec, a, st)));
+            rc = tc_launch_layer_pair(spec.kc, tc, L, spec, a, st);
         } else {
-            STPDE_TC_DISPATCH_KC(spec.kc, rc = launch_layer<KC>(tc, L, spec, a, st));
+            rc = tc_launch_layer(spec.kc, tc, L, spec, a, st);
         }
         if (rc) return rc;
     }
