@@ -213,23 +213,46 @@ class FusedJetQuery(torch.autograd.Function):
         grid, q, beta_t, *params = ctx.saved_tensors
         lo, hi, act, spec, n_layers, has_beta = ctx.meta
         needs = ctx.needs_input_grad
-        with torch.enable_grad():
-            grid_ = grid.detach().requires_grad_(needs[0])
-            q_ = q.detach().requires_grad_(needs[1])
-            beta_ = beta_t.detach().requires_grad_(needs[5]) if has_beta else None
-            params_ = [t.detach().requires_grad_(needs[9 + i]) for i, t in enumerate(params)]
-            y, jets = query_jets(grid_, q_, lo.to(q.device), hi.to(q.device), params_[:n_layers], params_[n_layers:],
-                                 act, beta_, spec)
-            outs, gouts = [y], [gy]
-            if jets is not None and gjets is not None and gjets.numel():
-                outs.append(jets)
-                gouts.append(gjets)
-            wanted = [(0, grid_)] * needs[0] + [(1, q_)] * needs[1] + ([(5, beta_)] if has_beta and needs[5] else [])
-            wanted += [(9 + i, t) for i, t in enumerate(params_) if needs[9 + i]]
-            grads = torch.autograd.grad(outs, [t for _, t in wanted], gouts, allow_unused=True) if wanted else []
         result = [None] * (9 + len(params))
-        for (slot, _), g in zip(wanted, grads):
+        if not any(needs):
+            return tuple(result)
+        # Points are independent, so the gradient is accumulated over chunks of the point dimension; the chunk is
+        # sized so that the autograd tape of the torch re-evaluation (~12 live tensors of rows x components x
+        # widest layer) stays below ~2 GB.
+        b, p, dim = q.shape
+        widest = max(int(t.shape[0]) for t in params[:n_layers])
+        per_point = (1 << dim) * (1 + len(spec.first) + len(spec.second)) * widest * 4 * 12 * b
+        step = max(64, min(p, int((2 << 30) // max(per_point, 1))))
+        lo_d, hi_d = lo.to(q.device), hi.to(q.device)
+        have_jets = spec.n_jet > 0 and gjets is not None and gjets.numel() > 0
+        acc = {}
+        q_grad = torch.zeros_like(q) if needs[1] else None
+        for s in range(0, p, step):
+            sl = slice(s, min(p, s + step))
+            with torch.enable_grad():
+                grid_ = grid.detach().requires_grad_(needs[0])
+                q_ = q[:, sl].detach().requires_grad_(needs[1])
+                beta_ = beta_t.detach().requires_grad_(needs[5]) if has_beta else None
+                params_ = [t.detach().requires_grad_(needs[9 + i]) for i, t in enumerate(params)]
+                y, jets = query_jets(grid_, q_, lo_d, hi_d, params_[:n_layers], params_[n_layers:], act, beta_, spec)
+                outs, gouts = [y], [gy[:, sl]]
+                if have_jets and jets is not None:
+                    outs.append(jets)
+                    gouts.append(gjets[:, :, sl])
+                wanted = [(0, grid_)] * needs[0] + [(1, q_)] * needs[1] + ([(5, beta_)] if has_beta and needs[5] else [])
+                wanted += [(9 + i, t) for i, t in enumerate(params_) if needs[9 + i]]
+                grads = torch.autograd.grad(outs, [t for _, t in wanted], gouts, allow_unused=True) if wanted else []
+            for (slot, _), g in zip(wanted, grads):
+                if g is None:
+                    continue
+                if slot == 1:
+                    q_grad[:, sl] = g
+                else:
+                    acc[slot] = g if slot not in acc else acc[slot] + g
+        for slot, g in acc.items():
             result[slot] = g
+        if needs[1]:
+            result[1] = q_grad
         return tuple(result)
 
 
