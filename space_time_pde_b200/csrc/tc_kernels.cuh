@@ -51,7 +51,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded: a protocol bug must surface as a trapped kernel (error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status) {
     uint32_t done = 0;
-    for (int spin = 0; spin < 400; ++spin) {                      // 400 x <= 10 ms
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -60,6 +61,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* st
             : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) return;
+        if ((spin & 63u) == 63u) {          // wall-clock bound (profilers / time slicing can stretch a wait a lot)
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) break;   // 20 s
+        }
     }
     atomicOr(status, 0x100);
     __trap();

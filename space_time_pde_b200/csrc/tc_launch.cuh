@@ -32,11 +32,13 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     constexpr int NR = tc::rows_per_tile(KC);
     constexpr int N = KC * NR;
     const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // bit per device: function attributes are per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!(configured >> (dev_ & 63) & 1ull)) {
         if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
-        configured = true;
+        configured |= 1ull << (dev_ & 63);
     }
     const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
@@ -49,11 +51,13 @@ static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const Je
                              cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // bit per device: function attributes are per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!(configured >> (dev_ & 63) & 1ull)) {
         if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
-        configured = true;
+        configured |= 1ull << (dev_ & 63);
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = tc.num_sms / 2;
