@@ -126,7 +126,11 @@ static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, co
     }
     for (int c = 1; c < s.kc; ++c) {
         if (c <= s.n_first) { s.kind[c] = 1; s.dir[c] = s.first_dirs[c - 1]; }
-        else { s.kind[c] = 2; s.pa[c] = s.sec_a[c - 1 - s.n_first]; s.pb[c] = s.sec_b[c - 1 - s.n_first]; }
+        else {
+            s.kind[c] = 2; s.pa[c] = s.sec_a[c - 1 - s.n_first]; s.pb[c] = s.sec_b[c - 1 - s.n_first];
+            s.sel_a[c][s.pa[c] - 1] = 1.f;
+            s.sel_b[c][s.pb[c] - 1] = 1.f;
+        }
     }
     // fixed workspace region
     size_t off = 256;  // status / scratch words

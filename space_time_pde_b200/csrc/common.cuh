@@ -33,6 +33,10 @@ struct JetSpec {
     int dir[STPDE_MAX_COMPONENTS];
     int pa[STPDE_MAX_COMPONENTS];
     int pb[STPDE_MAX_COMPONENTS];
+    // one-hot selectors of the parents over the first-order components 1..4 (all zero unless kind == 2):
+    // z_pa = sum_k sel_a[c][k] * z[1 + k] is 4 FFMAs with constant-bank operands instead of compare/select chains
+    float sel_a[STPDE_MAX_COMPONENTS][STPDE_MAX_FIRST];
+    float sel_b[STPDE_MAX_COMPONENTS][STPDE_MAX_FIRST];
 };
 
 // Geometry of the latent grid and the clip / cell arithmetic, all float32 exactly as the

@@ -342,27 +342,33 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     s2 *= fmask;
 #pragma unroll
                     for (int c = 1; c < KC; ++c) {
-                        float za = 0.f, zb = 0.f;
+                        float za = 0.f, zb = 0.f;        // parents of a second-order component (0 for first order)
 #pragma unroll
-                        for (int cc = 1; cc < KC; ++cc) {
-                            if (spec.kind[c] == 2 && cc == spec.pa[c]) za = zt[cc];
-                            if (spec.kind[c] == 2 && cc == spec.pb[c]) zb = zt[cc];
+                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                            if (1 + k < KC) {
+                                za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                            }
                         }
                         o[c] = fmaf(s2 * za, zb, s1 * zt[c]);    // first order: za = zb = 0
                     }
                     if (g_store && r < args.rows) {
                         const int64_t off = (int64_t)r * args.ld_out + g;
                         if (args.last) {
+                            float* pf = args.out_f32 + off;
 #pragma unroll
-                            for (int c = 0; c < KC; ++c) args.out_f32[off + c * plane] = o[c];
+                            for (int c = 0; c < KC; ++c) { *pf = o[c]; pf += plane; }
                         } else {
+                            __half* ph = args.out_hi + off;
+                            __half* pl = args.out_lo + off;
 #pragma unroll
                             for (int c = 0; c < KC; ++c) {
                                 const float xs = o[c] * act_scale;
                                 amax = fmaxf(amax, fabsf(xs));
                                 const __half hi = __float2half_rn(xs);
-                                args.out_hi[off + c * plane] = hi;
-                                if (three) args.out_lo[off + c * plane] = __float2half_rn(xs - __half2float(hi));
+                                *ph = hi;
+                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
+                                ph += plane; pl += plane;
                             }
                         }
                     }
@@ -731,27 +737,33 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                     s2 *= fmask;
 #pragma unroll
                     for (int c = 1; c < KC; ++c) {
-                        float za = 0.f, zb = 0.f;
+                        float za = 0.f, zb = 0.f;        // parents of a second-order component (0 for first order)
 #pragma unroll
-                        for (int cc = 1; cc < KC; ++cc) {
-                            if (spec.kind[c] == 2 && cc == spec.pa[c]) za = zt[cc];
-                            if (spec.kind[c] == 2 && cc == spec.pb[c]) zb = zt[cc];
+                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                            if (1 + k < KC) {
+                                za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                            }
                         }
                         o[c] = fmaf(s2 * za, zb, s1 * zt[c]);
                     }
                     if (g_store && r < args.rows) {
                         const int64_t off = (int64_t)r * args.ld_out + g;
                         if (args.last) {
+                            float* pf = args.out_f32 + off;
 #pragma unroll
-                            for (int c = 0; c < KC; ++c) args.out_f32[off + c * plane] = o[c];
+                            for (int c = 0; c < KC; ++c) { *pf = o[c]; pf += plane; }
                         } else {
+                            __half* ph = args.out_hi + off;
+                            __half* pl = args.out_lo + off;
 #pragma unroll
                             for (int c = 0; c < KC; ++c) {
                                 const float xs = o[c] * act_scale;
                                 amax = fmaxf(amax, fabsf(xs));
                                 const __half hi = __float2half_rn(xs);
-                                args.out_hi[off + c * plane] = hi;
-                                if (three) args.out_lo[off + c * plane] = __float2half_rn(xs - __half2float(hi));
+                                *ph = hi;
+                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
+                                ph += plane; pl += plane;
                             }
                         }
                     }
