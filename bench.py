@@ -127,6 +127,30 @@ def cpu_reference_rate(sample_pts, repeats=1, warm_pts=128):
     return sample_pts / best, best
 
 
+def gpu_eager_rate(device, batch=2048, batches=3):
+    """Reference algorithm (oracle/ref_port.py, autograd per dif) as PyTorch eager ops on the GPU, pseudo-batched
+    like the reference's evaluation loop (experiments/rb2d/evaluation.py:54-69)."""
+    from oracle import jet_oracle as jo
+    from oracle import ref_port as rp
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = make_model("cpu")
+    port = rp.SkipMLP([l.weight.detach().numpy() for l in model.fc], [l.bias.detach().numpy() for l in model.fc], ACT).to(device)
+    iv, ov, eqs = jo.rb2_equations(**RB2)
+    exprs = rp.compile_equations(eqs)
+    grid, q = synthetic_inputs(1234, device, batch * (batches + 1))
+    rp.values_and_residuals(port, grid, q[:, :batch], 0., 1., iv, ov, exprs)            # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, batches + 1):
+        y, res = rp.values_and_residuals(port, grid, q[:, i * batch:(i + 1) * batch], 0., 1., iv, ov, exprs)
+        del y, res
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": batch * batches / dt, "unit": UNIT,
+            "sample": f"{batches} pseudo-batches of {batch} points, torch eager fp32 on the same GPU (oracle/ref_port.py)"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -306,10 +330,14 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate, secs = cpu_reference_rate(1024, repeats=1)
+            rate, secs = cpu_reference_rate(8192, repeats=1)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1024 of {NPTS} points, {secs:.1f} s, oracle/ref_port.py (torch CPU, autograd per dif), "
+                   "sample": f"8192 of {NPTS} points, {secs:.1f} s, oracle/ref_port.py (torch CPU, autograd per dif), "
                              f"{cores} threads"}
+            try:   # context only: the same reference algorithm as PyTorch eager ops on this GPU (true fp32, no TF32)
+                eager = gpu_eager_rate(device)
+            except Exception as exc:   # e.g. out of memory for the autograd tapes
+                eager = {"error": str(exc)[:120]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -317,6 +345,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if cpu is not None:
+            line["torch_eager_gpu"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

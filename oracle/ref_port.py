@@ -63,19 +63,20 @@ class SkipMLP(torch.nn.Module):
 def lookup(grid, pts, xmin, xmax):
     """corner values, weights, relative coordinates (differentiable w.r.t. pts)."""
     dim = grid.dim() - 2
-    n = torch.tensor(grid.shape[1:-1]).float()
+    dev = grid.device
+    n = torch.tensor(grid.shape[1:-1]).float().to(dev)
     if isinstance(xmin, (int, float)) or isinstance(xmax, (int, float)):
-        xmin = float(xmin) * torch.ones(dim)
-        xmax = float(xmax) * torch.ones(dim)
+        xmin = float(xmin) * torch.ones(dim, device=dev)
+        xmax = float(xmax) * torch.ones(dim, device=dev)
     else:
-        xmin, xmax = torch.as_tensor(xmin), torch.as_tensor(xmax)
+        xmin, xmax = torch.as_tensor(xmin).to(dev), torch.as_tensor(xmax).to(dev)
     margin = 1e-6 * (xmax - xmin)
     pts = torch.max(torch.min(pts, xmax - margin), xmin + margin)
     h = (xmax - xmin) / (n - 1)
     lower = torch.floor(pts / h).long()
-    corners = torch.tensor(list(itertools.product((0, 1), repeat=dim)))           # [2^d, d]
+    corners = torch.tensor(list(itertools.product((0, 1), repeat=dim)), device=dev)   # [2^d, d]
     idx = lower.unsqueeze(2) + corners                                            # [b,p,2^d,d]
-    batch_idx = torch.arange(grid.shape[0]).view(-1, 1, 1).expand(idx.shape[:-1])
+    batch_idx = torch.arange(grid.shape[0], device=dev).view(-1, 1, 1).expand(idx.shape[:-1])
     values = grid[(batch_idx,) + tuple(idx[..., k] for k in range(dim))]
     node_lo = lower.float() * h
     node_hi = (lower.float() + 1) * h
