@@ -72,28 +72,32 @@ __global__ void gen_tables_kernel(JetSpec spec, int dim, int n0, int kp, const f
 }
 
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
-// One thread = 8 consecutive features of one row: 16-byte stores, coalesced 512 B per warp and plane.
+// One thread = 4 consecutive features of one row per iteration (8-byte stores, 256 B per warp and plane); the
+// per-feature constants live in registers, the next row's operands are prefetched while the current row is
+// evaluated (the kernel is latency-bound on the Vb gather otherwise).
 template <int KC>
-__global__ void __launch_bounds__(256, 2) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
-                                                             int ld, const int* __restrict__ vtx,
-                                                             const float* __restrict__ xrel, const float* __restrict__ Wx,
-                                                             const float* __restrict__ Vb, int ncat, int three, int fast_act,
-                                                             __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                             int* __restrict__ status) {
+__global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
+                                                                int ld, const int* __restrict__ vtx,
+                                                                const float* __restrict__ xrel, const float* __restrict__ Wx,
+                                                                const float* __restrict__ Vb, int ncat, int three,
+                                                                __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                                int* __restrict__ status) {
+    constexpr int F = 4;
     const int fg = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int n0 = (blockIdx.x * 32 + fg) * 8;
+    const int n0 = (blockIdx.x * 32 + fg) * F;
     if (n0 >= ld) return;
-    float wx[8][kMaxDim];
+    float wx[F][kMaxDim];
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < F; ++e)
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) wx[e][k] = (k < dim && n0 + e < N) ? __ldg(Wx + (n0 + e) * dim + k) : 0.f;
     const float act_scale = (float)(1 << tc::kActScaleLog2);
-    // per-feature constants of the closed-form layer-0 jets (row independent): a_c = sigma^(order) * coef[c]
-    float coef[KC][8];
+    // a_c = sigma^(order_c)(z0) * coef[c]: coef = 2^4 (value), W0x[:,dir] * 2^4, W0x[:,a] * W0x[:,b] * 2^4; 0 for pad features
+    float coef[KC][F];
+    float cmax = 0.f, smax = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const float fm = (n0 + e < N) ? act_scale : 0.f;      // pad features -> 0; fold the fp16 scale in
+    for (int e = 0; e < F; ++e) {
+        const float fm = (n0 + e < N) ? act_scale : 0.f;
         coef[0][e] = fm;
 #pragma unroll
         for (int c = 1; c < KC; ++c) {
@@ -106,59 +110,72 @@ __global__ void __launch_bounds__(256, 2) layer0_jets_tc_kernel(JetSpec spec, in
             }
             coef[c][e] = wa * wb * fm;
         }
+#pragma unroll
+        for (int c = 0; c < KC; ++c) cmax = fmaxf(cmax, fabsf(coef[c][e]));
     }
-    float cmax = 0.f, smax = 0.f;      // overflow guard: |a_c| <= max|sigma^(k)| * max|coef|
+    const bool vec_ok = (n0 + F <= N) && (ncat % 4 == 0);
+    const int n_first = spec.n_first;
+    auto load_row = [&](int r, float* xr, float* vb) {
+        const int rc = min(r, rows - 1);
 #pragma unroll
-    for (int c = 0; c < KC; ++c)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cmax = fmaxf(cmax, fabsf(coef[c][e]));
-    const bool vec_ok = (n0 + 8 <= N) && (ncat % 4 == 0);
-    for (int j = 0; j < 8; ++j) {
-        const int r = blockIdx.y * 64 + rl + 8 * j;
-        if (r >= rows) break;
-        float xr[kMaxDim];
-#pragma unroll
-        for (int k = 0; k < kMaxDim; ++k) xr[k] = k < dim ? __ldg(xrel + (int64_t)k * rows + r) : 0.f;
-        const float* vrow = Vb + (int64_t)__ldg(vtx + r) * ncat + n0;
-        float vb[8];
+        for (int k = 0; k < kMaxDim; ++k) xr[k] = __ldg(xrel + (int64_t)k * rows + rc);     // planes >= dim are zero
+        const float* vrow = Vb + (int64_t)__ldg(vtx + rc) * ncat + n0;
         if (vec_ok) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(vrow));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(vrow) + 1);
-            vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w; vb[4] = b.x; vb[5] = b.y; vb[6] = b.z; vb[7] = b.w;
+            vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) vb[e] = (n0 + e < N) ? __ldg(vrow + e) : 0.f;
+            for (int e = 0; e < F; ++e) vb[e] = (n0 + e < N) ? __ldg(vrow + e) : 0.f;
         }
-        float o[KC][8];
+    };
+    float xr[kMaxDim], vb[F];
+    const int rbase = blockIdx.y * 64 + rl;
+    if (rbase < rows) load_row(rbase, xr, vb);
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const int r = rbase + 8 * j;
+        if (r >= rows) break;
+        float xr_n[kMaxDim], vb_n[F];
+        load_row(r + 8, xr_n, vb_n);                      // prefetch (clamped to a valid row)
+        float s0[F], s1[F], s2[F];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < F; ++e) {
             float z = vb[e];
 #pragma unroll
-            for (int k = 0; k < kMaxDim; ++k)
-                if (k < dim) z = fmaf(wx[e][k], xr[k], z);
-            float s0, s1, s2;
-            act_jet_fast(act, beta, z, s0, s1, s2);
-            smax = fmaxf(smax, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))));
-            o[0][e] = s0 * coef[0][e];
-#pragma unroll
-            for (int c = 1; c < KC; ++c) o[c][e] = (spec.kind[c] == 1 ? s1 : s2) * coef[c][e];
+            for (int k = 0; k < kMaxDim; ++k) z = fmaf(wx[e][k], xr[k], z);
+            act_jet_fast(act, beta, z, s0[e], s1[e], s2[e]);
+            smax = fmaxf(smax, fmaxf(fabsf(s0[e]), fmaxf(fabsf(s1[e]), fabsf(s2[e]))));
         }
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
-            uint32_t ph[4], pl[4];
+            float x[F];
+            if (c == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                const float x0 = o[c][e], x1 = o[c][e + 1];
-                const __half2 h = __floats2half2_rn(x0, x1);
+                for (int e = 0; e < F; ++e) x[e] = s0[e] * coef[c][e];
+            } else if (c <= n_first) {                    // warp-uniform branch instead of per-element selects
+#pragma unroll
+                for (int e = 0; e < F; ++e) x[e] = s1[e] * coef[c][e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < F; ++e) x[e] = s2[e] * coef[c][e];
+            }
+            uint32_t ph[F / 2], pl[F / 2];
+#pragma unroll
+            for (int e = 0; e < F; e += 2) {
+                const __half2 h = __floats2half2_rn(x[e], x[e + 1]);
                 const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                const __half2 l = __floats2half2_rn(x[e] - hf.x, x[e + 1] - hf.y);
                 ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
                 pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
             }
             const int64_t off = ((int64_t)c * rows + r) * ld + n0;
-            *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (three) *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(ph[0], ph[1]);
+            if (three) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pl[0], pl[1]);
         }
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k) xr[k] = xr_n[k];
+#pragma unroll
+        for (int e = 0; e < F; ++e) vb[e] = vb_n[e];
     }
     if (!(smax * cmax < 65000.f)) atomicOr(status, kStatusRange);
 }
@@ -312,9 +329,9 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
 template <int KC>
 static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
-    dim3 grid((tc.ld0 + 255) / 256, (cb.rows + 63) / 64);
+    dim3 grid((tc.ld0 + 127) / 128, (cb.rows + 63) / 64);
     layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
-                                                    tc.passes == 3, tc.fast_act, tc.act[0][0], tc.act[0][1], tc.status);
+                                                    tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
 }
 
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,

@@ -382,3 +382,50 @@ def test_wide_decoder_jets_vs_oracle(case, dev, precision):
     if spec.n_jet:
         for plane, ref in zip(jt.cpu().numpy(), _oracle_planes(yj, spec)):
             assert metric(plane, ref) < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded shape fuzz: odd channel counts / widths / outputs / grid sizes against the fp64 oracle
+# ---------------------------------------------------------------------------------------------
+def _fuzz_cases():
+    import random
+    rnd = random.Random(20261017)
+    cases = []
+    for i in range(14):
+        dim = rnd.choice([1, 2, 3, 3, 3, 4])
+        gshape = tuple(rnd.choice([2, 3, 5, 7]) for _ in range(dim))
+        c = rnd.choice([1, 3, 5, 8, 13, 32])
+        o = rnd.choice([1, 2, 3, 4, 5, 8])
+        nf = rnd.choice([1, 3, 4, 7, 16, 24, 32])
+        act = rnd.choice(["tanh", "softplus", "swish", "elu", "softplus"])
+        dirs = sorted(rnd.sample(range(dim), rnd.randint(0, dim)))
+        pairs = [(a, b) for a in dirs for b in dirs if a <= b]
+        second = tuple(sorted(rnd.sample(pairs, rnd.randint(0, min(len(pairs), 5))))) if pairs else ()
+        cases.append((i, dim, gshape, c, o, nf, act, tuple(dirs), second, rnd.choice([1, 2, 3]), rnd.choice([1, 37, 200])))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: f"fuzz{c[0]}_d{c[1]}_c{c[3]}_o{c[4]}_nf{c[5]}_{c[6]}_K{1 + len(c[7]) + len(c[8])}")
+def test_shape_fuzz_vs_oracle(case, dev, precision):
+    i, dim, gshape, c, o, nf, act, first, second, batch, npts = case
+    torch.manual_seed(1000 + i)
+    model = sp.ImNet(dim=dim, in_features=c, out_features=o, nf=nf, activation=sp.NONLINEARITIES[act]).to(dev)
+    grid = torch.randn(batch, *gshape, c, device=dev) * 0.6
+    q = torch.rand(batch, npts, dim, device=dev)
+    spec = JetSpec(first, second)
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), act, model.activ.beta if act == "swish" else None,
+                               spec=spec)
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    beta = float(model.activ.beta.detach()) if act == "swish" else 1.0
+    yj = jo.query_jet(grid.cpu().numpy(), q.cpu().numpy(), 0., 1., Ws, bs, act, beta)
+    tol = TOL * (3 if dim == 4 and precision == "fp16x3" else 1)
+    metric = rel_err_quantile if act == "elu" else rel_linf
+    assert rel_linf(y.cpu().numpy(), yj.v) < tol
+    if spec.n_jet:
+        for plane, ref in zip(jt.cpu().numpy(), _oracle_planes(yj, spec)):
+            if np.max(np.abs(ref)) < 1e-12:
+                assert np.max(np.abs(plane)) < 1e-6
+            else:
+                assert metric(plane, ref) < tol
