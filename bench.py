@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("STPDE_PRECISION", "fp16x3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=1,
+                    help="timed training steps (forward + residuals + loss + fused backward [+ all-reduce]); 0 skips the leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,6 +326,57 @@ def main():
                         "fp32 FFMA and fp16x3 execute more than the algorithmic FLOPs, the fraction is of the "
                         "measured bf16 tensor peak"}
 
+    # ---- training step: forward + residuals + L1 losses + fused CUDA backward to the latent grid
+    #      and the decoder weights, then ONE all-reduce of [loss sums | counts | flat gradients] ----
+    train = None
+    if args.train_steps > 0:
+        from space_time_pde_b200.parallel import StepReducer
+        grid_t = grid.clone().requires_grad_(True)
+        params = [grid_t] + list(model.parameters())
+        for p_ in params[1:]:
+            p_.requires_grad_(True)
+        reducer = StepReducer(params)
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid_t, pts, 0., 1.))
+
+        def train_step():
+            for p_ in params:
+                p_.grad = None
+            y, res = layer(q, return_residue=True)
+            reg = y.abs().sum()
+            pde = torch.stack(list(res.values())).abs().sum()
+            (reg / (world * y.numel()) + 0.0125 * pde / (world * 4 * NPTS)).backward()
+            return reducer.reduce({"reg": reg, "pde": pde}, {"reg": y.numel(), "pde": 4 * NPTS})
+
+        train_step()
+        barrier()
+        lib.stpde_profile_enable(1)
+        _lib.profile_read()
+        tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tv0.record()
+        for _ in range(args.train_steps):
+            means = train_step()
+        tv1.record()
+        barrier()
+        prof_t = _lib.profile_read()
+        lib.stpde_profile_enable(0)
+        tms = torch.tensor([tv0.elapsed_time(tv1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        tms = float(tms.item()) / args.train_steps
+        # algorithmic FLOPs of a training step = 3 x the forward contractions (forward, dgrad, wgrad); the recompute
+        # of the forward inside the backward is overhead, not counted
+        train = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
+                 "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients)"
+                         + (" + one NCCL all-reduce of the flat gradient buffer" if world > 1 else ""),
+                 "algorithmic_tflops": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12,
+                 "frac_of_peak": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12 / peaks["tflops"],
+                 "loss_reg": float(means["reg"]), "loss_pde": float(means["pde"]),
+                 "kernel_ms_per_step": {k: v[0] / args.train_steps for k, v in prof_t.items() if v[1] > 0},
+                 "gpu_launches_per_step": int(sum(v[1] for v in prof_t.values()) / args.train_steps)}
+        for p_ in params:
+            p_.grad = None
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -344,7 +397,7 @@ def main():
                 "config": workload_config(args.precision), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "train_step": train}
         if cpu is not None:
             line["torch_eager_gpu"] = eager
         print(json.dumps(line), flush=True)

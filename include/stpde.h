@@ -15,6 +15,10 @@
  *                                 + src/pde.py:8-9,115-143 PDELayer.__call__ / torch_diff
  *                                 (values and every partial derivative the equation strings need,
  *                                  in ONE pass: forward-mode jets instead of autograd.grad per dif())
+ *   stpde_jet_backward         <- the loss.backward() sweep through the three items above
+ *                                 (experiments/rb2d/train.py:77; src/pde.py:8 create_graph=True makes the
+ *                                 reference differentiate THROUGH every autograd.grad call): gradients w.r.t. the
+ *                                 decoder weights / biases and the latent grid in one reverse sweep over the jets
  *   stpde_residuals            <- src/pde.py:139-142 (evaluation of the lambdified equations)
  *   stpde_jet_forward_host     <- same as stpde_jet_forward with HOST buffers (copies inside)
  *
@@ -38,7 +42,7 @@
 extern "C" {
 #endif
 
-#define STPDE_VERSION 100 /* major*10000 + minor*100 + patch */
+#define STPDE_VERSION 200 /* major*10000 + minor*100 + patch */
 
 #define STPDE_MAX_DIM 4
 #define STPDE_MAX_LAYERS 8
@@ -107,7 +111,7 @@ typedef struct stpde_desc {
     int32_t precision;
     float xmin[STPDE_MAX_DIM];          /* float32 bounds exactly as the reference forms them */
     float xmax[STPDE_MAX_DIM];
-    int32_t reserved[8];
+    int32_t reserved[8];                /* [0]: backward only, extra headroom bits of the adjoint scale (0 = default) */
 } stpde_desc_t;
 
 int stpde_version(void);
@@ -151,6 +155,28 @@ int stpde_jet_forward(const stpde_desc_t *desc, const float *grid, const int64_t
                       const float *q, const int64_t *q_strides, const float *const *W,
                       const float *const *B, float *y, float *jets, void *workspace,
                       size_t workspace_bytes, int32_t *status, void *stream);
+
+/*
+ * Reverse mode of stpde_jet_forward: given gy = d loss / d y [b,p,o] and gjets = d loss / d jets
+ * [n_first + n_second, b, p, o] (contiguous; gjets may be NULL when no derivatives were requested), writes
+ *   gW[l] : [widths[l], in_l]  gradient of layer l's weight      (host array of n_layers device pointers)
+ *   gB[l] : [widths[l]]        gradient of layer l's bias
+ *   ggrid : [b, n_1..n_d, c]   gradient of the latent grid, CONTIGUOUS (may be NULL)
+ * All outputs are overwritten.  The forward is recomputed per chunk of points (no activations are kept between
+ * the forward and the backward call); the contractions run on the tensor cores with the fp16 hi/lo split
+ * (STPDE_PREC_FP32 and STPDE_PREC_FP16X3: 3 passes, STPDE_PREC_FP16: 1 pass).  Needs n_layers >= 3.
+ * Gradients w.r.t. the query points and w.r.t. act_param are not produced.
+ * status bit 1 reports an adjoint that left the fp16 range.  The adjoints are rescaled by a power of two S derived
+ * from max|gy|, max|gjets| so that the bound on the blended adjoints sits at 2^(10 - desc->reserved[0]); when the
+ * flag comes back the caller repeats the call with reserved[0] += 6 (more headroom, less precision for tiny
+ * adjoints).
+ */
+size_t stpde_backward_workspace_bytes(const stpde_desc_t *desc);
+int stpde_jet_backward(const stpde_desc_t *desc, const float *grid, const int64_t *grid_strides,
+                       const float *q, const int64_t *q_strides, const float *const *W,
+                       const float *const *B, const float *gy, const float *gjets, float *const *gW,
+                       float *const *gB, float *ggrid, void *workspace, size_t workspace_bytes,
+                       int32_t *status, void *stream);
 
 /*
  * Same computation with HOST buffers (grid, q, weights, y, jets all in host memory; grid and q

@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libstpde.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "simt_kernels.cu", "tc_path.cu", "tc_layers_a.cu", "tc_layers_b.cu", "tc_layers_c.cu", "profile.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "bwd_kernels.cu", "tc_path.cu", "tc_bwd.cu", "tc_layers_a.cu", "tc_layers_b.cu",
+           "tc_layers_c.cu", "tc_bwd_a.cu", "tc_bwd_b.cu", "tc_bwd_c.cu", "profile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -46,6 +47,7 @@ class StpdeDesc(ctypes.Structure):
 
 EXPORTS = ["stpde_version", "stpde_last_error", "stpde_desc_size", "stpde_device_sm_count", "stpde_workspace_bytes",
            "stpde_interp_coefficients", "stpde_interp", "stpde_jet_forward", "stpde_jet_forward_host",
+           "stpde_backward_workspace_bytes", "stpde_jet_backward",
            "stpde_residuals", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
 
 
@@ -116,6 +118,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.stpde_jet_forward.argtypes = [descp, c_void_p, i64p, c_void_p, i64p, ctypes.POINTER(c_void_p),
                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
                                       c_void_p]
+    lib.stpde_backward_workspace_bytes.restype = c_size_t
+    lib.stpde_backward_workspace_bytes.argtypes = [descp]
+    lib.stpde_jet_backward.restype = c_int
+    lib.stpde_jet_backward.argtypes = [descp, c_void_p, i64p, c_void_p, i64p, ctypes.POINTER(c_void_p),
+                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
     lib.stpde_jet_forward_host.restype = c_int
     lib.stpde_jet_forward_host.argtypes = [descp, c_void_p, c_void_p, ctypes.POINTER(c_void_p),
                                            ctypes.POINTER(c_void_p), c_void_p, c_void_p]
@@ -152,7 +160,7 @@ def load() -> ctypes.CDLL:
 def profile_read():
     """{slot name: (milliseconds, launches)} since the previous read (synchronises the device)."""
     lib = load()
-    n = 12
+    n = 16
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_int64 * n)()
     lib.stpde_profile_read(ms, cnt, n)

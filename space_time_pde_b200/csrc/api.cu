@@ -6,8 +6,10 @@
 #include <cstring>
 #include <vector>
 
+#include "bwd_kernels.h"
 #include "kernels.h"
 #include "profile.h"
+#include "tc_bwd.h"
 #include "tc_path.h"
 
 namespace stpde {
@@ -68,6 +70,9 @@ struct Plan {
     int64_t total_pts;
     // workspace layout
     size_t off_wh[kMaxLayers], off_wx[kMaxLayers], off_vb, off_tc, fixed_bytes, per_point_bytes;
+    // reverse mode (always on the tensor cores): fixed region = [0, off_tc) as above, then the split weights and
+    // their transposes, the adjoint of Vb and the scale scratch
+    size_t off_bwd_gvb, off_bwd_scale, bwd_fixed_bytes, bwd_per_point_bytes;
 };
 
 static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, const int64_t* qstrides) {
@@ -161,6 +166,16 @@ static int make_plan(Plan& P, const stpde_desc_t* d, const int64_t* gstrides, co
                              tc_per_point_bytes(P.n_layers, P.widths, kc, P.ncorner);
     else
         P.per_point_bytes += (size_t)kc * P.ncorner * 4 * ((size_t)P.max_even + P.max_odd);
+    {
+        size_t boff = align_up(P.off_tc + (P.n_layers >= 3 ? tc_bwd_fixed_bytes(P.n_layers, P.widths) : 0), 1024);
+        P.off_bwd_gvb = boff;
+        boff = align_up(boff + (size_t)(P.nvert_total > 0 ? P.nvert_total : 1) * P.ncat * sizeof(float), 1024);
+        P.off_bwd_scale = boff;
+        P.bwd_fixed_bytes = boff + 1024;
+        P.bwd_per_point_bytes = (size_t)P.ncorner * (4 + 4 * kMaxDim) + (size_t)4 * 5 * d->dim +
+                                (size_t)kc * P.ncorner * 4 * P.np[P.n_layers - 2] +
+                                (P.n_layers >= 3 ? tc_bwd_per_point_bytes(P.n_layers, P.widths, kc, P.ncorner) : 0);
+    }
     return STPDE_OK;
 }
 
@@ -277,6 +292,147 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     return STPDE_OK;
 }
 
+static size_t bwd_chunk_region_bytes(const Plan& P, int64_t pc) { return (size_t)pc * P.bwd_per_point_bytes + 64 * 1024; }
+
+static int64_t default_bwd_chunk_points(const Plan& P) {
+    size_t budget_mb = 6144;
+    if (const char* e = getenv("STPDE_WORKSPACE_MB")) budget_mb = (size_t)atoll(e);
+    int64_t pc = (int64_t)((budget_mb << 20) / (P.bwd_per_point_bytes ? P.bwd_per_point_bytes : 1));
+    pc = pc / 128 * 128;
+    int64_t need = (P.total_pts + 127) / 128 * 128;
+    if (pc > need) pc = need;
+    if (pc < 128) pc = 128;
+    return pc;
+}
+
+// Reverse-mode sweep: gradients of  sum(gy * y) + sum(gjets * jets)  w.r.t. the decoder weights / biases and the
+// latent grid.  Per chunk of points: recompute the forward keeping every operand plane, then blend_backward ->
+// (wgrad, dgrad) per hidden layer on the tensor cores; the per-vertex adjoint gVb is folded into the latent-column
+// weights, the biases and the grid once at the end.
+static int run_backward(const Plan& P, const stpde_desc_t* d, const float* grid, const float* q, const float* const* W,
+                        const float* const* B, const float* gy, const float* gjets, float* const* gW, float* const* gB,
+                        float* ggrid, char* ws, size_t ws_bytes, int* status, cudaStream_t st) {
+    const int dim = d->dim, kc = P.spec.kc, L = P.n_layers - 1;
+    for (int l = 0; l < P.n_layers; ++l) {
+        CUDA_TRY(cudaMemsetAsync(gW[l], 0, (size_t)P.widths[l] * P.in_features[l] * sizeof(float), st));
+        CUDA_TRY(cudaMemsetAsync(gB[l], 0, (size_t)P.widths[l] * sizeof(float), st));
+    }
+    if (ggrid) CUDA_TRY(cudaMemsetAsync(ggrid, 0, (size_t)P.nvert_total * d->channels * sizeof(float), st));
+    if (P.total_pts == 0) return STPDE_OK;
+    if (ws_bytes < P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128))
+        return fail(STPDE_ENOMEM, "workspace %zu B < minimum %zu B", ws_bytes, P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128));
+    int64_t pc = (int64_t)((ws_bytes - P.bwd_fixed_bytes - 64 * 1024) / P.bwd_per_point_bytes) / 128 * 128;
+    int64_t need = (P.total_pts + 127) / 128 * 128;
+    if (pc > need) pc = need;
+    if (pc > (1 << 22)) pc = 1 << 22;
+    const int64_t rows = pc * P.ncorner;
+    if (rows * (int64_t)P.np64[0] * kc >= (int64_t)1 << 40 || rows >= ((int64_t)1 << 31))
+        return fail(STPDE_EUNSUPPORTED, "chunk too large");
+
+    char* p = ws + P.bwd_fixed_bytes;
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+    ChunkBuffers cb;
+    cb.pc = (int)pc;
+    cb.rows = (int)rows;
+    cb.vtx = (int*)take(rows * 4);
+    cb.xrel = (float*)take((size_t)kMaxDim * rows * 4);
+    cb.wfac = (float*)take((size_t)dim * 2 * pc * 4);
+    cb.dfac = (float*)take((size_t)dim * 2 * pc * 4);
+    cb.dxr = (float*)take((size_t)dim * pc * 4);
+    const int np_last = P.np[P.n_layers - 2];
+    float* act_last = (float*)take((size_t)kc * rows * np_last * 4);
+    p = (char*)align_up((size_t)p, 1024);
+    char* tc_chunk = p;
+
+    NetDesc net;
+    memset(&net, 0, sizeof(net));
+    net.n_layers = P.n_layers;
+    net.ncat = P.ncat;
+    for (int l = 0; l < P.n_layers; ++l) {
+        net.cat_off[l] = P.cat_off[l];
+        net.in_features[l] = P.in_features[l];
+        net.kh[l] = P.kh[l];
+        net.W[l] = W[l];
+        net.B[l] = B[l];
+    }
+    float* Vb = (float*)(ws + P.off_vb);
+    float* g_vb = (float*)(ws + P.off_bwd_gvb);
+    unsigned* maxes = (unsigned*)(ws + P.off_bwd_scale);
+    float* scale = (float*)(ws + P.off_bwd_scale + 256);
+    const float* Wx[kMaxLayers] = {nullptr};
+    prof_begin(kSlotSetup, st);
+    for (int l = 0; l < P.n_layers; ++l) {
+        float* wx = l < L ? (float*)(ws + P.off_wx[l]) : nullptr;
+        Wx[l] = wx;
+        if (l == L) launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, P.widths[l], P.kp[l], (float*)(ws + P.off_wh[l]), nullptr, st);
+        else launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, 0, 1, nullptr, wx, st);
+    }
+    launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
+    CUDA_TRY(cudaMemsetAsync(g_vb, 0, (size_t)P.nvert_total * P.ncat * sizeof(float), st));
+    // reserved[0] = headroom bits below the default adjoint scale (the binding retries with more headroom when the
+    // range flag comes back)
+    int target_exp = 10 - d->reserved[0];
+    target_exp = target_exp > 14 ? 14 : (target_exp < -40 ? -40 : target_exp);
+    launch_grad_scale(P.spec, P.geom, gy, kc > 1 ? gjets : nullptr, P.total_pts * P.O, maxes, scale, target_exp, st);
+    prof_end(kSlotSetup, st, P.n_layers + 4);
+
+    TcBwdContext tc;
+    int rc = tc_bwd_prepare(tc, d->precision, P.n_layers, P.widths, P.in_features, W, ws + P.off_tc, tc_chunk,
+                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, st);
+    if (rc) return fail(rc, "%s", tc_last_error());
+
+    const TcBwdLayer& TL = tc.layer[P.n_layers - 2];
+    for (int64_t p0 = 0; p0 < P.total_pts; p0 += pc) {
+        {
+            ProfScope ps(kSlotPrep, st);
+            launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
+        }
+        rc = tc_bwd_forward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, Wx, act_last,
+                                  np_last, st);
+        if (rc) return fail(rc, "%s", tc_last_error());
+        {
+            BlendBwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.dim = dim; a.rows = cb.rows; a.O = P.O; a.Kp = P.kp[L]; a.n_feat = P.widths[L - 1];
+            a.ld_out = TL.ldz; a.ldz = TL.ldz; a.act = d->act_kind; a.beta = d->act_param;
+            a.ncat = P.ncat; a.cat_off = P.cat_off[L - 1]; a.three = tc.passes == 3;
+            a.total_pts = P.total_pts; a.p0 = p0; a.cb = cb;
+            a.gy = gy; a.gjets = gjets; a.scale = scale;
+            a.Wlast = (const float*)(ws + P.off_wh[L]);
+            a.act_last = act_last; a.z_in = TL.z;
+            a.out_hi = TL.zb[0]; a.out_lo = TL.zb[1];
+            a.g_vb = g_vb;
+            a.g_wx = gW[L - 1] + P.kh[L - 1]; a.g_wx_ld = P.in_features[L - 1];
+            a.g_wlast = gW[L]; a.g_blast = gB[L];
+            a.status = status;
+            ProfScope ps(kSlotBwdBlend, st);
+            rc = launch_blend_backward(P.spec, a, st);
+            if (rc) return fail(rc, "blend_backward: decoder too wide for the shared-memory staging");
+        }
+        rc = tc_bwd_backward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, P.in_features, Wx,
+                                   gW, g_vb, st);
+        if (rc) return fail(rc, "%s", tc_last_error());
+    }
+    {
+        ProfScope ps(kSlotBwdVertex, st, 3 + 2 * P.n_layers);
+        VertexBwdArgs v;
+        memset(&v, 0, sizeof(v));
+        v.n_layers = P.n_layers; v.ncat = P.ncat;
+        for (int l = 0; l < P.n_layers; ++l) {
+            v.cat_off[l] = P.cat_off[l]; v.in_features[l] = P.in_features[l]; v.kh[l] = P.kh[l];
+            v.W[l] = W[l]; v.gW[l] = gW[l]; v.gB[l] = gB[l];
+        }
+        v.grid = grid; v.g_vb = g_vb; v.scale = scale;
+        launch_vertex_backward(P.geom, P.nvert_total, v, ggrid, st);
+        for (int l = 0; l < P.n_layers; ++l) {
+            launch_scale_buffer(gW[l], (int64_t)P.widths[l] * P.in_features[l], scale, st);
+            launch_scale_buffer(gB[l], P.widths[l], scale, st);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STPDE_OK;
+}
+
 }  // namespace stpde
 
 using namespace stpde;
@@ -334,6 +490,29 @@ int stpde_jet_forward(const stpde_desc_t* desc, const float* grid, const int64_t
     if (!grid || !q || !W || !B || !y || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
     if (P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
     return run_forward(P, desc, grid, q, W, B, y, jets, (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
+}
+
+size_t stpde_backward_workspace_bytes(const stpde_desc_t* desc) {
+    Plan P;
+    if (make_plan(P, desc, nullptr, nullptr) != STPDE_OK) return 0;
+    if (P.n_layers < 3) { fail(STPDE_EUNSUPPORTED, "the fused backward needs at least 3 linear layers"); return 0; }
+    return P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, default_bwd_chunk_points(P));
+}
+
+int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_t* grid_strides, const float* q,
+                       const int64_t* q_strides, const float* const* W, const float* const* B, const float* gy,
+                       const float* gjets, float* const* gW, float* const* gB, float* ggrid, void* workspace,
+                       size_t workspace_bytes, int32_t* status, void* stream) {
+    Plan P;
+    int rc = make_plan(P, desc, grid_strides, q_strides);
+    if (rc) return rc;
+    if (P.n_layers < 3) return fail(STPDE_EUNSUPPORTED, "the fused backward needs at least 3 linear layers");
+    if (!grid || !q || !W || !B || !gy || !gW || !gB || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
+    if (P.spec.kc > 1 && !gjets) return fail(STPDE_EINVAL, "gjets required when derivatives were requested");
+    for (int l = 0; l < P.n_layers; ++l)
+        if (!W[l] || !B[l] || !gW[l] || !gB[l]) return fail(STPDE_EINVAL, "null weight / gradient pointer for layer %d", l);
+    return run_backward(P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, (char*)workspace, workspace_bytes, status,
+                        (cudaStream_t)stream);
 }
 
 int stpde_jet_forward_host(const stpde_desc_t* desc, const float* grid, const float* q, const float* const* W,

@@ -1,0 +1,391 @@
+// CUDA-core kernels of the reverse-mode (training) sweep: everything that is not a big contraction.
+//
+//   grad_scale      : power-of-two scale S for the adjoints (they travel through fp16 hi/lo operand planes)
+//   blend_backward  : transpose of final_blend (product rule over the 2^d corners) + last linear layer
+//                     + reverse jet activation of the last hidden layer
+//   vertex_backward : adjoint of the per-vertex precompute Vb = b + W[:, latent cols] . latent
+//   scale_buffer    : final 1/S
+// Mirrors the forward kernels of simt_kernels.cu; see DESIGN.md "Reverse mode".
+#include <cuda_fp16.h>
+
+#include "bwd_kernels.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace stpde {
+
+// ----------------------------------------------------------------------------------------------
+// adjoint scale
+// ----------------------------------------------------------------------------------------------
+// maxes[plane] = max |g| over plane 0 = gy, plane 1.. = gjets planes (non-negative floats order like uints)
+__global__ void absmax_planes_kernel(const float* __restrict__ gy, const float* __restrict__ gjets, int64_t plane_elems,
+                                     int n_planes, unsigned* __restrict__ maxes) {
+    const int pl = blockIdx.y;
+    if (pl >= n_planes) return;
+    const float* src = pl == 0 ? gy : gjets + (int64_t)(pl - 1) * plane_elems;
+    float m = 0.f;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < plane_elems; e += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(src[e]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxes + pl, __float_as_uint(m));
+}
+
+// Bound on |d loss / d out_c| of any corner: the blend multiplies the incoming adjoints by weights <= 1 and by
+// d x_rel / d q = 1 / cubesize per derivative order.  scale[0] = S = 2^(target_exp - ceil(log2 bound)), scale[1] = 1 / S.
+// The adjoints live in fp16 hi/lo planes (|x| < 65504, lo goes subnormal below 2^-14): a large target keeps small
+// adjoints precise, the headroom 2^(16 - target_exp) absorbs their growth through the transposed weights.
+__global__ void grad_scale_kernel(JetSpec spec, GridGeom g, const unsigned* __restrict__ maxes, float* __restrict__ scale,
+                                  int target_exp) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float bound = __uint_as_float(maxes[0]);
+    for (int c = 1; c < spec.kc; ++c) {
+        float m = __uint_as_float(maxes[c]);
+        if (spec.kind[c] == 1) m *= 1.f / g.cubesize[spec.dir[c]];
+        else m *= (1.f / g.cubesize[spec.dir[spec.pa[c]]]) * (1.f / g.cubesize[spec.dir[spec.pb[c]]]);
+        bound += m;
+    }
+    float S = 1.f;
+    if (bound > 0.f && bound < 3.0e38f) {
+        int e2 = 0;
+        frexpf(bound, &e2);             // bound = m * 2^e2, m in [0.5, 1)
+        int sh = target_exp - e2;
+        sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+        S = ldexpf(1.f, sh);
+    }
+    scale[0] = S;
+    scale[1] = 1.f / S;
+}
+
+__global__ void scale_buffer_kernel(float* __restrict__ buf, int64_t n, const float* __restrict__ scale) {
+    const float s = scale[1];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) buf[e] *= s;
+}
+
+// W^T hi/lo [fp rows (f)][ldz (g)] = fp16 split of W[g][f] * 2^sw (the forward's per-layer scale, from its absmax)
+__global__ void split_weights_t_kernel(const float* __restrict__ W, int N, int in_features, int kh, int fp, int ldz,
+                                       const unsigned* __restrict__ absmax, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float amax = __uint_as_float(*absmax);
+    int e2 = 0;
+    if (amax > 0.f) frexpf(amax, &e2);
+    const int sw = amax > 0.f ? 14 - e2 : 0;
+    const float up = ldexpf(1.f, sw);
+    const int64_t total = (int64_t)fp * ldz;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(e / ldz), g = (int)(e % ldz);
+        const float x = (g < N && f < kh) ? W[(int64_t)g * in_features + f] * up : 0.f;
+        const __half h = __float2half_rn(x);
+        hi[e] = h;
+        lo[e] = __float2half_rn(x - __half2float(h));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// blend_backward: one CTA = 128 (point, corner) rows, like final_blend.
+//   phase 1  ob[c][row][o] = d loss / d out_c  (transpose of the product-rule blend), scaled by S
+//   phase 2  abar_c[f] = sum_o Wlast[o][f] ob_c[o] -> reverse jet activation with the saved z of the last hidden
+//            layer -> zbar planes (fp16 hi/lo, the dgrad / wgrad operands), adjoints of Vb, of the coordinate
+//            columns, of the last layer's weight and bias
+// ----------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, BlendBwdArgs a) {
+    extern __shared__ float sm[];
+    const int O = a.O, Kp = a.Kp, F = a.n_feat, ldo = a.ld_out, dim = a.dim;
+    float* Ws = sm;                          // [O][Kp]
+    float* ob = Ws + O * Kp;                 // [KC][128][O]
+    float* gWl = ob + KC * 128 * O;          // [O][ldo]
+    float* gWx = gWl + O * ldo;              // [ldo][dim]
+    float* gB = gWx + ldo * dim;             // [O]
+    const int ncorner = 1 << dim;
+    const int row0 = blockIdx.x * 128;
+    const float S = a.scale[0];
+    for (int e = threadIdx.x; e < O * Kp; e += blockDim.x) Ws[e] = a.Wlast[e];
+    for (int e = threadIdx.x; e < KC * 128 * O; e += blockDim.x) ob[e] = 0.f;
+    for (int e = threadIdx.x; e < O * ldo + ldo * dim + O; e += blockDim.x) gWl[e] = 0.f;
+    __syncthreads();
+
+    // ---- phase 1: one thread per (local row, output); it owns ob[.][lr][o] ----
+    for (int e = threadIdx.x; e < 128 * O; e += blockDim.x) {
+        const int o = e % O, lr = e / O;
+        const int lp = lr / ncorner, j = lr % ncorner;
+        const int i = row0 / ncorner + lp;
+        const int64_t gp = a.p0 + i;
+        if (i >= a.cb.pc || gp >= a.total_pts) continue;
+        float w = 1.f;
+        float fk[kMaxDim], dk[kMaxDim], dx[kMaxDim];
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k) {
+            fk[k] = 1.f; dk[k] = 0.f; dx[k] = 0.f;
+            if (k < dim) {
+                const int bit = (j >> (dim - 1 - k)) & 1;
+                fk[k] = a.cb.wfac[(k * 2 + bit) * a.cb.pc + i];
+                dk[k] = a.cb.dfac[(k * 2 + bit) * a.cb.pc + i];
+                dx[k] = a.cb.dxr[k * a.cb.pc + i];
+                w *= fk[k];
+            }
+        }
+        for (int c = 0; c < KC; ++c) {
+            const float gin = S * (c == 0 ? a.gy[gp * O + o] : a.gjets[((int64_t)(c - 1) * a.total_pts + gp) * O + o]);
+            const int kind = spec.kind[c];
+            if (kind == 0) { ob[lr * O + o] += w * gin; continue; }
+            const int ca = kind == 2 ? spec.pa[c] : c, cbi = kind == 2 ? spec.pb[c] : c;
+            const int da = kind == 1 ? spec.dir[c] : spec.dir[ca], db = spec.dir[cbi];
+            float wa = 1.f, wb = 1.f, wab = 1.f, dxa = 0.f, dxb = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) {
+                if (k < dim) {
+                    wa *= (k == da) ? dk[k] : fk[k];
+                    wb *= (k == db) ? dk[k] : fk[k];
+                    wab *= (k == da || k == db) ? dk[k] : fk[k];
+                }
+                if (k == da) dxa = dx[k];
+                if (k == db) dxb = dx[k];
+            }
+            if (kind == 1) {
+                ob[lr * O + o] += wa * gin;
+                ob[(c * 128 + lr) * O + o] += w * dxa * gin;
+            } else {
+                ob[lr * O + o] += (da == db ? 0.f : wab) * gin;
+                ob[(cbi * 128 + lr) * O + o] += wa * dxb * gin;
+                ob[(ca * 128 + lr) * O + o] += wb * dxa * gin;
+                ob[(c * 128 + lr) * O + o] += w * dxa * dxb * gin;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: (local row, feature) items ----
+    const int64_t zplane = (int64_t)a.rows * a.ldz, aplane = (int64_t)a.rows * Kp, oplane = (int64_t)a.rows * ldo;
+    float amax = 0.f;
+    for (int e = threadIdx.x; e < 128 * ldo; e += blockDim.x) {
+        const int f = e % ldo, lr = e / ldo;
+        const int r = row0 + lr;
+        if (r >= a.rows) continue;
+        float zb[KC];
+        if (f < F) {
+            float z[KC], ab[KC], av[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                z[c] = a.z_in[(int64_t)c * zplane + (int64_t)r * a.ldz + f];
+                av[c] = a.act_last[(int64_t)c * aplane + (int64_t)r * Kp + f];
+                float s = 0.f;
+                for (int o = 0; o < O; ++o) s = fmaf(Ws[o * Kp + f], ob[(c * 128 + lr) * O + o], s);
+                ab[c] = s;
+            }
+            for (int o = 0; o < O; ++o) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) s = fmaf(ob[(c * 128 + lr) * O + o], av[c], s);
+                atomicAdd(gWl + o * ldo + f, s);
+            }
+            float s1, s2, s3;
+            act_d123_fast(a.act, a.beta, z[0], s1, s2, s3);
+            jet_act_backward<KC>(spec, s1, s2, s3, z, ab, zb);
+            const int vrow = a.cb.vtx[r];
+            atomicAdd(a.g_vb + (int64_t)vrow * a.ncat + a.cat_off + f, zb[0]);
+            for (int k = 0; k < dim; ++k) {
+                float s = zb[0] * a.cb.xrel[(int64_t)k * a.rows + r];
+#pragma unroll
+                for (int c = 1; c < KC; ++c)
+                    if (spec.kind[c] == 1 && spec.dir[c] == k) s += zb[c];
+                atomicAdd(gWx + f * dim + k, s);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < KC; ++c) zb[c] = 0.f;
+        }
+        const int64_t off = (int64_t)r * ldo + f;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            const float xs = zb[c];
+            amax = fmaxf(amax, fabsf(xs));
+            const __half hi = __float2half_rn(xs);
+            a.out_hi[(int64_t)c * oplane + off] = hi;
+            if (a.three) a.out_lo[(int64_t)c * oplane + off] = __float2half_rn(xs - __half2float(hi));
+        }
+    }
+    if (!(amax < 65000.f)) atomicOr(a.status, kStatusRange);
+    for (int e = threadIdx.x; e < 128 * O; e += blockDim.x) {
+        if (row0 + e / O < a.rows) atomicAdd(gB + e % O, ob[e]);      // component 0 only: the bias enters the value
+    }
+    __syncthreads();
+
+    // ---- flush the CTA's partial sums ----
+    for (int e = threadIdx.x; e < O * ldo; e += blockDim.x) {
+        const int o = e / ldo, f = e % ldo;
+        if (f < F) atomicAdd(a.g_wlast + (int64_t)o * F + f, gWl[e]);
+    }
+    for (int e = threadIdx.x; e < F * dim; e += blockDim.x)
+        atomicAdd(a.g_wx + (int64_t)(e / dim) * a.g_wx_ld + e % dim, gWx[e]);
+    for (int e = threadIdx.x; e < O; e += blockDim.x) atomicAdd(a.g_blast + e, gB[e]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// vertex_backward (weights): gb_l[n] = sum_v gVb[v][cat],  gW_l[n][kh + dim + ch] = sum_v gVb[v][cat] latent[v][ch]
+// block = 128 cats x one slice of 256 vertices; channel tiles of 32 keep the accumulators in registers
+// ----------------------------------------------------------------------------------------------
+constexpr int kVbSlice = 256;
+
+__global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int nvert_total, VertexBwdArgs a) {
+    __shared__ float lat[16][33];
+    const int cat = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = cat < a.ncat;
+    int l = 0;
+    if (ok) while (l + 1 < a.n_layers - 1 && cat >= a.cat_off[l + 1]) ++l;
+    const int n = cat - a.cat_off[l];
+    const int v_begin = blockIdx.y * kVbSlice, v_end = min(v_begin + kVbSlice, nvert_total);
+    const int c = g.channels;
+    float bsum = 0.f;
+    for (int ct = 0; ct < c; ct += 32) {
+        float acc[32];
+#pragma unroll
+        for (int ch = 0; ch < 32; ++ch) acc[ch] = 0.f;
+        for (int v0 = v_begin; v0 < v_end; v0 += 16) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < 16 * 32; e += blockDim.x) {
+                const int vi = e / 32, ch = ct + e % 32;
+                const int v = v0 + vi;
+                float val = 0.f;
+                if (v < v_end && ch < c) {
+                    const int b = v / g.nvert;
+                    int rem = v % g.nvert;
+                    int64_t off = b * g.gstride[0] + ch * g.gstride[g.dim + 1];
+                    for (int k = g.dim - 1; k >= 0; --k) {
+                        off += (rem % g.size[k]) * g.gstride[1 + k];
+                        rem /= g.size[k];
+                    }
+                    val = a.grid[off];
+                }
+                lat[vi][e % 32] = val;
+            }
+            __syncthreads();
+            if (ok) {
+#pragma unroll 4
+                for (int vi = 0; vi < 16; ++vi) {
+                    if (v0 + vi >= v_end) break;
+                    const float gv = a.g_vb[(int64_t)(v0 + vi) * a.ncat + cat];
+                    if (ct == 0) bsum += gv;
+#pragma unroll
+                    for (int ch = 0; ch < 32; ++ch) acc[ch] = fmaf(gv, lat[vi][ch], acc[ch]);
+                }
+            }
+        }
+        if (ok) {
+            float* dst = a.gW[l] + (int64_t)n * a.in_features[l] + a.kh[l] + g.dim + ct;
+#pragma unroll
+            for (int ch = 0; ch < 32; ++ch)
+                if (ct + ch < c) atomicAdd(dst + ch, acc[ch]);
+        }
+    }
+    if (ok) atomicAdd(a.gB[l] + n, bsum);
+}
+
+// vertex_backward (latent grid): ggrid[v][ch] = (1/S) sum_cat gVb[v][cat] * W_l(cat)[n(cat)][kh + dim + ch]
+// block = 8 vertices x 32 channels, cat tiles of 128 staged in shared memory
+__global__ void __launch_bounds__(256) vertex_backward_grid_kernel(GridGeom g, int nvert_total, VertexBwdArgs a,
+                                                                   float* __restrict__ ggrid) {
+    __shared__ float gv[8][128];
+    __shared__ const float* wrow[128];
+    const int ch = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int vi = threadIdx.x >> 5;
+    const int v = blockIdx.x * 8 + vi;
+    const int c = g.channels;
+    float acc = 0.f;
+    for (int cat0 = 0; cat0 < a.ncat; cat0 += 128) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 8 * 128; e += blockDim.x) {
+            const int vv = blockIdx.x * 8 + e / 128, cat = cat0 + e % 128;
+            gv[e / 128][e % 128] = (vv < nvert_total && cat < a.ncat) ? a.g_vb[(int64_t)vv * a.ncat + cat] : 0.f;
+        }
+        if (threadIdx.x < 128) {
+            const int cat = cat0 + threadIdx.x;
+            const float* p = nullptr;
+            if (cat < a.ncat) {
+                int l = 0;
+                while (l + 1 < a.n_layers - 1 && cat >= a.cat_off[l + 1]) ++l;
+                p = a.W[l] + (int64_t)(cat - a.cat_off[l]) * a.in_features[l] + a.kh[l] + g.dim;
+            }
+            wrow[threadIdx.x] = p;
+        }
+        __syncthreads();
+        if (ch < c) {
+            const int lim = min(128, a.ncat - cat0);
+            for (int t = 0; t < lim; ++t) acc = fmaf(gv[vi][t], __ldg(wrow[t] + ch), acc);
+        }
+    }
+    if (v < nvert_total && ch < c) ggrid[(int64_t)v * c + ch] = acc * a.scale[1];
+}
+
+// ----------------------------------------------------------------------------------------------
+// launchers
+// ----------------------------------------------------------------------------------------------
+static inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g > 148 * 8) g = 148 * 8;
+    return (int)(g < 1 ? 1 : g);
+}
+
+void launch_grad_scale(const JetSpec& spec, const GridGeom& g, const float* gy, const float* gjets, int64_t plane_elems,
+                       unsigned* maxes, float* scale, int target_exp, cudaStream_t st) {
+    cudaMemsetAsync(maxes, 0, sizeof(unsigned) * kMaxComp, st);
+    const int n_planes = gjets ? spec.kc : 1;
+    dim3 grid(grid_for(plane_elems, 256), n_planes);
+    absmax_planes_kernel<<<grid, 256, 0, st>>>(gy, gjets, plane_elems, n_planes, maxes);
+    grad_scale_kernel<<<1, 32, 0, st>>>(spec, g, maxes, scale, target_exp);
+}
+
+void launch_scale_buffer(float* buf, int64_t n, const float* scale, cudaStream_t st) {
+    if (n <= 0) return;
+    scale_buffer_kernel<<<grid_for(n, 256), 256, 0, st>>>(buf, n, scale);
+}
+
+void launch_split_weights_t(const float* W, int N, int in_features, int kh, int fp, int ldz, const unsigned* absmax,
+                            __half* hi, __half* lo, cudaStream_t st) {
+    split_weights_t_kernel<<<148 * 4, 256, 0, st>>>(W, N, in_features, kh, fp, ldz, absmax, hi, lo);
+}
+
+size_t blend_backward_smem(int kc, int O, int Kp, int ldo, int dim) {
+    return (size_t)(O * Kp + kc * 128 * O + O * ldo + ldo * dim + O) * sizeof(float);
+}
+
+template <int KC>
+static int launch_blend_backward_t(const JetSpec& spec, const BlendBwdArgs& a, cudaStream_t st) {
+    const size_t smem = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim);
+    if (smem > 200 * 1024) return STPDE_EUNSUPPORTED;
+    static unsigned long long configured = 0;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!(configured >> (dev_ & 63) & 1ull)) {
+        cudaFuncSetAttribute(blend_backward_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured |= 1ull << (dev_ & 63);
+    }
+    blend_backward_kernel<KC><<<(a.rows + 127) / 128, 256, smem, st>>>(spec, a);
+    return STPDE_OK;
+}
+
+int launch_blend_backward(const JetSpec& spec, const BlendBwdArgs& a, cudaStream_t st) {
+    int rc = STPDE_OK;
+    switch (spec.kc) {
+        case 1: rc = launch_blend_backward_t<1>(spec, a, st); break;
+        case 2: rc = launch_blend_backward_t<2>(spec, a, st); break;
+        case 3: rc = launch_blend_backward_t<3>(spec, a, st); break;
+        case 4: rc = launch_blend_backward_t<4>(spec, a, st); break;
+        case 5: rc = launch_blend_backward_t<5>(spec, a, st); break;
+        case 6: rc = launch_blend_backward_t<6>(spec, a, st); break;
+        case 7: rc = launch_blend_backward_t<7>(spec, a, st); break;
+        case 8: rc = launch_blend_backward_t<8>(spec, a, st); break;
+        case 9: rc = launch_blend_backward_t<9>(spec, a, st); break;
+        default: rc = launch_blend_backward_t<10>(spec, a, st); break;
+    }
+    return rc;
+}
+
+void launch_vertex_backward(const GridGeom& g, int nvert_total, const VertexBwdArgs& a, float* ggrid, cudaStream_t st) {
+    dim3 gw((a.ncat + 127) / 128, (nvert_total + kVbSlice - 1) / kVbSlice);
+    vertex_backward_w_kernel<<<gw, 128, 0, st>>>(g, nvert_total, a);
+    if (ggrid) {
+        dim3 gg((nvert_total + 7) / 8, (g.channels + 31) / 32);
+        vertex_backward_grid_kernel<<<gg, 256, 0, st>>>(g, nvert_total, a, ggrid);
+    }
+}
+
+}  // namespace stpde

@@ -145,6 +145,87 @@ __device__ __forceinline__ void act_jet_fast(int kind, float beta, float z, floa
     }
 }
 
+// sigma', sigma'', sigma''' (MUFU-based): the reverse-mode sweep through a second-order jet needs the third
+// derivative (d a_kl / d z_0 = sigma''' z_k z_l + sigma'' z_kl).  Same branch conventions as act_jet_fast.
+__device__ __forceinline__ void act_d123_fast(int kind, float beta, float z, float& s1, float& s2, float& s3) {
+    switch (kind) {
+        case STPDE_ACT_TANH: {
+            const float e = __expf(2.f * z);
+            const float t = 1.f - __fdividef(2.f, 1.f + e);
+            const float u = 1.f - t * t;
+            s1 = u; s2 = -2.f * t * u; s3 = -2.f * u * (1.f - 3.f * t * t);
+            break;
+        }
+        case STPDE_ACT_RELU: {
+            s1 = z > 0.f ? 1.f : 0.f; s2 = 0.f; s3 = 0.f;
+            break;
+        }
+        case STPDE_ACT_LEAKYRELU: {
+            s1 = z > 0.f ? 1.f : 0.01f; s2 = 0.f; s3 = 0.f;
+            break;
+        }
+        case STPDE_ACT_SOFTPLUS: {
+            const bool lin = z > 20.f;
+            const float e = __expf(fminf(z, 20.f));
+            const float r = __fdividef(1.f, 1.f + e);
+            const float s = e * r;
+            s1 = lin ? 1.f : s;
+            s2 = lin ? 0.f : s * r;
+            s3 = lin ? 0.f : s * r * (1.f - 2.f * s);
+            break;
+        }
+        case STPDE_ACT_ELU: {
+            const bool neg = z <= 0.f;
+            const float e = __expf(fminf(z, 0.f));
+            s1 = neg ? e : 1.f; s2 = neg ? e : 0.f; s3 = neg ? e : 0.f;
+            break;
+        }
+        default: {  // STPDE_ACT_SWISH
+            const float bz = beta * z;
+            const float s = __fdividef(1.f, 1.f + __expf(-bz));
+            const float ds = s * (1.f - s);
+            const float m = 1.f - 2.f * s;
+            s1 = s + bz * ds;
+            s2 = beta * ds * (2.f + bz * m);
+            s3 = beta * beta * ds * (m * (3.f + bz * m) - 2.f * bz * ds);
+            break;
+        }
+    }
+}
+
+// Reverse-mode sweep through the jet activation of one (row, feature):
+//   forward   o_0 = s0(z_0),  o_k = s1 z_k (first order),  o_c = s2 z_a z_b + s1 z_c (second order, parents a, b)
+//   backward  zb_c = d loss / d z_c  from  ob_c = d loss / d o_c
+// sel_a / sel_b are the one-hot parent selectors of JetSpec (all zero for first-order components).
+template <int KC>
+__device__ __forceinline__ void jet_act_backward(const JetSpec& spec, float s1, float s2, float s3, const float* z,
+                                                 const float* ob, float* zb) {
+    float z0b = s1 * ob[0];
+    float cross[STPDE_MAX_FIRST];
+#pragma unroll
+    for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+#pragma unroll
+    for (int c = 1; c < KC; ++c) {
+        float za = 0.f, zbp = 0.f;
+#pragma unroll
+        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+            if (1 + k < KC) {
+                za = fmaf(spec.sel_a[c][k], z[1 + k], za);
+                zbp = fmaf(spec.sel_b[c][k], z[1 + k], zbp);
+            }
+        }
+        z0b = fmaf(ob[c], fmaf(s3 * za, zbp, s2 * z[c]), z0b);
+        zb[c] = s1 * ob[c];
+#pragma unroll
+        for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+            if (1 + k < KC) cross[k] = fmaf(ob[c], fmaf(spec.sel_a[c][k], zbp, spec.sel_b[c][k] * za), cross[k]);
+    }
+    zb[0] = z0b;
+#pragma unroll
+    for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+        if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
+}
+
 // runtime switch used by the tensor-core kernels: accurate (libdevice) in the fp32-parity mode fp16x3 unless
 // STPDE_TC_FAST_ACT=1, MUFU-based in the relaxed single-pass fp16 mode
 __device__ __forceinline__ void act_jet_sel(bool fast, int kind, float beta, float z, float& s0, float& s1, float& s2) {

@@ -17,7 +17,7 @@ std::vector<Pair> g_free;
 int64_t g_launches[kNumSlots] = {0};
 const char* kNames[kNumSlots] = {"setup", "prep_points", "layer0_jets", "gemm_layer1", "gemm_layer2", "gemm_layer3",
                                  "gemm_layer4", "gemm_layer5", "gemm_layer6", "gemm_layer7", "final_blend",
-                                 "residuals"};
+                                 "residuals", "bwd_blend", "bwd_wgrad", "bwd_dgrad", "bwd_vertex"};
 }  // namespace
 
 void prof_begin(int slot, cudaStream_t st) {

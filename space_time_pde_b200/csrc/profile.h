@@ -12,7 +12,11 @@ enum ProfSlot {
     kSlotGemm = 3,      // kSlotGemm + (l - 1) for hidden layer l = 1..7
     kSlotFinal = 10,    // last linear layer + blend
     kSlotResidual = 11, // residual programs
-    kNumSlots = 12
+    kSlotBwdBlend = 12, // reverse: blend + last layer + last hidden activation
+    kSlotWgrad = 13,    // reverse: weight-gradient contractions
+    kSlotDgrad = 14,    // reverse: activation-gradient contractions + reverse jet activation
+    kSlotBwdVertex = 15,// reverse: per-vertex adjoint -> latent columns, biases, grid; final 1/S
+    kNumSlots = 16
 };
 
 void prof_begin(int slot, cudaStream_t st);

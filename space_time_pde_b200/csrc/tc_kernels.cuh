@@ -170,7 +170,20 @@ struct LayerArgs {
     __half* out_lo;
     float* out_f32;        // [KC][rows][ld_out]
     int* status;
+    // ---- training (save) / reverse-mode fields (tc_layer_pair_kernel MODE 1..3) ----
+    float* z_out;          // MODE 1: pre-activations of this layer, fp32 [KC][rows][ldz]
+    const float* z_in;     // MODE 2: pre-activations of the layer whose adjoints this launch produces
+    int ldz;               // row stride of z_out / z_in
+    float* g_vb;           // MODE 2/3: adjoint of Vb, [nvert][ncat] (atomics)
+    float* g_wx;           // MODE 2/3: adjoint of the coordinate columns, &gW[0][kh], row stride g_wx_ld (atomics)
+    int g_wx_ld;
 };
+
+// kernel modes of tc_layer_pair_kernel
+constexpr int kModeFwd = 0;       // forward layer (inference)
+constexpr int kModeFwdSave = 1;   // forward layer that also stores its pre-activations (recompute pass of the backward)
+constexpr int kModeBwd = 2;       // dgrad of layer l (W_l^T . zbar_l) + reverse jet activation of layer l-1 >= 1
+constexpr int kModeBwd0 = 3;      // dgrad of layer 1 + reverse of the closed-form layer 0
 
 template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -453,7 +466,7 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
 // planes but GENERATED in shared memory by 8 generator warps from the closed-form layer-0 jets
 // (a_c = sigma^(k)(z0) * coef_c, z0 = Vb0[vertex] + W0x . x_rel), written in the SWIZZLE_128B K-major layout the
 // UMMA descriptors expect.  This removes layer 0's HBM round trip (412 GB / step at BASELINE config 2).
-template <int KC, bool GEN>
+template <int KC, bool GEN, int MODE = kModeFwd>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -672,7 +685,129 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp < 2 + kEpiW) {
+    } else if (MODE >= kModeBwd && warp < 2 + kEpiW) {
+        // ===================== reverse-mode epilogue =====================
+        // The accumulator holds S * 2^sw * abar[c][r][g]: the adjoint of the activations of the layer BELOW the
+        // contraction (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with
+        // the saved z planes and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the
+        // closed-form layer 0 (nothing below it: only the parameter adjoints are accumulated).
+        const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
+        const int64_t plane = (int64_t)args.rows * args.ld_out;
+        const int64_t zplane = (int64_t)args.rows * args.ldz;
+        const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
+        int it = 0;
+        for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
+            const int buf = it & 1;
+            const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
+            const int g = f0 + quarter * 32 + lane;
+            const bool g_store = g < args.n_store;
+            const bool g_ok = g < args.n_feat;
+            float gx[kMaxDim];
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) gx[k] = 0.f;
+            float wx[kMaxDim];                                      // MODE 3: layer-0 coordinate columns of this feature
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k)
+                wx[k] = (MODE == kModeBwd0 && k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
+            float amax = 0.f;
+#pragma unroll 1
+            for (int rb = sub; rb < NRB; rb += kEpiPQ) {
+                uint32_t v[KC][8];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + rb * 8 + i;
+                    const bool r_ok = r < args.rows;
+                    const int rc = min(r, args.rows - 1);
+                    const int vrow = __ldg(args.vtx + rc);
+                    float xr[kMaxDim];
+#pragma unroll
+                    for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
+                    float ab[KC];
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][i]) * scale : 0.f;
+                    float z0b;
+                    if constexpr (MODE == kModeBwd) {
+                        float z[KC], zb[KC];
+#pragma unroll
+                        for (int c = 0; c < KC; ++c)
+                            z[c] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
+                        float s1, s2, s3;
+                        act_d123_fast(args.act, args.beta, z[0], s1, s2, s3);
+                        jet_act_backward<KC>(spec, s1, s2, s3, z, ab, zb);
+                        z0b = zb[0];
+#pragma unroll
+                        for (int c = 1; c < KC; ++c)
+#pragma unroll
+                            for (int k = 0; k < kMaxDim; ++k)
+                                if (spec.kind[c] == 1 && spec.dir[c] == k) gx[k] += zb[c];
+                        if (g_store && r_ok) {
+                            const int64_t off = (int64_t)r * args.ld_out + g;
+                            __half* ph = args.out_hi + off;
+                            __half* pl = args.out_lo + off;
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) {
+                                const float xs = zb[c];
+                                amax = fmaxf(amax, fabsf(xs));
+                                const __half hi = __float2half_rn(xs);
+                                *ph = hi;
+                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
+                                ph += plane; pl += plane;
+                            }
+                        }
+                    } else {
+                        // layer 0: a_c = sigma^(order_c)(z0) * coef_c, coef = 1 | W0x[dir] | W0x[dir_a] * W0x[dir_b]
+                        float z0 = g_ok ? __ldg(args.Vb + (int64_t)vrow * args.ncat + args.cat_off + g) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < kMaxDim; ++k) z0 = fmaf(wx[k], xr[k], z0);
+                        float s1, s2, s3;
+                        act_d123_fast(args.act, args.beta, z0, s1, s2, s3);
+                        z0b = 0.f;
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) {
+                            float wa = 1.f, wb = 1.f;
+#pragma unroll
+                            for (int k = 0; k < kMaxDim; ++k) {
+                                if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
+                                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
+                                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
+                            }
+                            const float sd = spec.kind[c] == 0 ? s1 : spec.kind[c] == 1 ? s2 : s3;   // d a_c / d z0
+                            const float sl = spec.kind[c] == 0 ? 0.f : spec.kind[c] == 1 ? s1 : s2;  // d a_c / d coef_c
+                            z0b = fmaf(ab[c] * sd, wa * wb, z0b);
+                            const float t = ab[c] * sl;
+#pragma unroll
+                            for (int k = 0; k < kMaxDim; ++k) {
+                                if (spec.kind[c] == 1 && k == spec.dir[c]) gx[k] += t;
+                                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) gx[k] = fmaf(t, wb, gx[k]);
+                                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) gx[k] = fmaf(t, wa, gx[k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kMaxDim; ++k) gx[k] = fmaf(z0b, xr[k], gx[k]);
+                    if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+                }
+            }
+            if (g_ok) {
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, gx[k]);
+            }
+            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+        }
+    } else if (MODE < kModeBwd && warp < 2 + kEpiW) {
         // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
@@ -732,6 +867,15 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
                     act_jet_fast(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    if constexpr (MODE == kModeFwdSave) {
+                        if (g < args.n_feat && r < args.rows) {     // pre-activations for the reverse sweep
+                            const int64_t zplane = (int64_t)args.rows * args.ldz;
+                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
+                            *pz = zt[0] + zs[i];
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
+                        }
+                    }
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;

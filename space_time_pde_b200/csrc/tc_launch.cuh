@@ -66,6 +66,29 @@ static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const Je
     return STPDE_OK;
 }
 
+// CTA-pair kernel in one of the training modes (tc_kernels.cuh kMode*): the maps are passed explicitly because the
+// reverse sweep runs the same kernel on W^T / zbar planes.  Always the pair kernel: TMA zero-fills the feature
+// rows beyond the layer width.
+template <int KC, int MODE>
+static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                                  const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
+    static unsigned long long configured = 0;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!(configured >> (dev_ & 63) & 1ull)) {
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel, training mode) failed");
+        configured |= 1ull << (dev_ & 63);
+    }
+    const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
+    const int max_pairs = num_sms / 2;
+    const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
+    tc::tc_layer_pair_kernel<KC, false, MODE><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    return STPDE_OK;
+}
+
 #endif  // STPDE_TC_LAUNCH_IMPL
 
 }  // namespace stpde

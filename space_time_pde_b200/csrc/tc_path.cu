@@ -1,5 +1,6 @@
 // Host orchestration + small helper kernels of the tensor-core path.
 #include "tc_path.h"
+#include "tc_bwd.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -250,6 +251,20 @@ static int make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uin
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// helpers shared with the reverse-mode path (tc_bwd.cu)
+int tc_make_map_2d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1) {
+    return make_map_2d(m, base, d0, d1, b0, b1);
+}
+int tc_make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2) {
+    return make_map_3d(m, base, d0, d1, d2, b0, b1, b2);
+}
+bool tc_encode_available() { return encode_fn() != nullptr; }
+void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int np, int kp, unsigned* absmax,
+                             float* wscale, __half* hi, __half* lo, cudaStream_t st) {
+    absmax_kernel<<<148, 256, 0, st>>>(W, N, in_features, kh, absmax);
+    split_weights_kernel<<<148 * 4, 256, 0, st>>>(W, N, in_features, kh, np, kp, absmax, wscale, hi, lo);
+}
+
 int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
                int* status, cudaStream_t st) {
@@ -332,6 +347,15 @@ static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, 
     dim3 grid((tc.ld0 + 127) / 128, (cb.rows + 63) / 64);
     layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
                                                     tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
+}
+
+void tc_launch_layer0_planes(int kc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
+                             const float* Wx, const float* Vb, int ncat, int three, __half* out_hi, __half* out_lo,
+                             int* status, cudaStream_t st) {
+    dim3 grid((ld + 127) / 128, (cb.rows + 63) / 64);
+    STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
+                                                                              cb.xrel, Wx, Vb, ncat, three, out_hi, out_lo,
+                                                                              status)));
 }
 
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,

@@ -191,8 +191,73 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
     return y, jets
 
 
+def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
+                 Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
+                 spec: JetSpec, precision: str, gy: torch.Tensor, gjets: Optional[torch.Tensor],
+                 need_grid: bool = True, check: bool = True):
+    """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l]).
+
+    Replaces what ``loss.backward()`` does in the reference (experiments/rb2d/train.py:77) for the decode +
+    PDE-derivative part of the graph: autograd's backward through every ``torch.autograd.grad`` call of
+    src/pde.py:8 (create_graph=True) and through src/local_implicit_grid.py:47-61.
+    """
+    lib = _lib.load()
+    device = q.device
+    Wc = [w.detach().to(device=device, dtype=torch.float32).contiguous() for w in Ws]
+    Bc = [v.detach().to(device=device, dtype=torch.float32).contiguous() for v in bs]
+    widths = [w.shape[0] for w in Wc]
+    gy = gy.detach().to(torch.float32).contiguous()
+    if spec.n_jet:
+        gjets = gjets.detach().to(torch.float32).contiguous()
+    gW = [torch.empty_like(w) for w in Wc]
+    gB = [torch.empty_like(v) for v in Bc]
+    ggrid = torch.empty(grid.shape, dtype=torch.float32, device=device) if need_grid else None
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    wptr = (ctypes.c_void_p * len(Wc))(*[w.data_ptr() for w in Wc])
+    bptr = (ctypes.c_void_p * len(Bc))(*[v.data_ptr() for v in Bc])
+    gwptr = (ctypes.c_void_p * len(gW))(*[w.data_ptr() for w in gW])
+    gbptr = (ctypes.c_void_p * len(gB))(*[v.data_ptr() for v in gB])
+    gstr, qstr = _i64(grid.stride()), _i64(q.stride())
+    sync = check and os.environ.get("STPDE_ASYNC", "0") != "1"
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        desc = make_desc(grid, q, lo, hi, widths, act, act_param, spec, precision)
+        nbytes = lib.stpde_backward_workspace_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            raise _lib.StpdeError(-1, lib.stpde_last_error().decode())
+        ws = _workspace(device, nbytes)
+        # The adjoints travel through fp16 hi/lo planes behind a power-of-two scale; if one overflows (status bit 1)
+        # the sweep is repeated with 6 more bits of headroom.
+        for headroom in (0, 6, 12, 24):
+            desc.reserved[0] = headroom
+            status.zero_()
+            rc = lib.stpde_jet_backward(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr, bptr,
+                                        gy.data_ptr(), gjets.data_ptr() if spec.n_jet else None, gwptr, gbptr,
+                                        ggrid.data_ptr() if ggrid is not None else None, ws.data_ptr(), ws.numel(),
+                                        status.data_ptr(), stream)
+            _lib.check(rc)
+            if not sync or not (int(status.item()) & 2):
+                break
+        else:
+            raise _lib.StpdeError(-6, "an adjoint left the fp16 range of the split-precision tensor-core backward; "
+                                      "set STPDE_BACKWARD=torch to use the autograd re-evaluation")
+    return ggrid, gW, gB
+
+
+def fused_backward_supported(q: torch.Tensor, spec: JetSpec, n_layers: int, needs_q: bool, needs_beta: bool) -> bool:
+    """The CUDA reverse sweep covers grid / weight / bias gradients of decoders with >= 3 linear layers."""
+    if os.environ.get("STPDE_BACKWARD", "fused") == "torch":
+        return False
+    return (q.is_cuda and n_layers >= 3 and not needs_q and not needs_beta
+            and 1 + len(spec.first) + len(spec.second) <= _lib.MAX_COMPONENTS)
+
+
 class FusedJetQuery(torch.autograd.Function):
-    """(grid, q, *params) -> (y, jets).  Backward re-evaluates the jets with torch ops (see _torch_jets.py)."""
+    """(grid, q, *params) -> (y, jets).
+
+    Backward: ``stpde_jet_backward`` (fused CUDA reverse sweep) for the gradients w.r.t. the latent grid and the
+    decoder weights / biases; gradients w.r.t. the query points or a learnable Swish beta (not needed by the
+    reference training loop) re-evaluate the jets with differentiable torch ops (see _torch_jets.py)."""
 
     @staticmethod
     def forward(ctx, grid, q, lo, hi, act, act_param_t, spec, precision, n_layers, *params):
@@ -201,6 +266,7 @@ class FusedJetQuery(torch.autograd.Function):
         y, jets = raw_forward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision)
         ctx.save_for_backward(grid, q, act_param_t if act_param_t is not None else torch.empty(0), *params)
         ctx.meta = (lo, hi, act, spec, n_layers, act_param_t is not None)
+        ctx.precision = precision
         if jets is None:
             jets = y.new_empty(0)
             ctx.mark_non_differentiable(jets)
@@ -215,6 +281,19 @@ class FusedJetQuery(torch.autograd.Function):
         needs = ctx.needs_input_grad
         result = [None] * (9 + len(params))
         if not any(needs):
+            return tuple(result)
+        if fused_backward_supported(q, spec, n_layers, needs[1], has_beta and needs[5]):
+            beta = float(beta_t.detach()) if has_beta else 1.0
+            gj = gjets if (spec.n_jet > 0 and gjets is not None and gjets.numel() > 0) else None
+            if spec.n_jet > 0 and gj is None:
+                gj = torch.zeros(spec.n_jet, *gy.shape, dtype=gy.dtype, device=gy.device)
+            ggrid, gW, gB = raw_backward(grid, q, lo, hi, params[:n_layers], params[n_layers:], act, beta, spec,
+                                         ctx.precision, gy, gj, need_grid=needs[0])
+            if needs[0]:
+                result[0] = ggrid
+            for i, g in enumerate(list(gW) + list(gB)):
+                if needs[9 + i]:
+                    result[9 + i] = g.to(params[i].dtype)
             return tuple(result)
         # Points are independent, so the gradient is accumulated over chunks of the point dimension; the chunk is
         # sized so that the autograd tape of the torch re-evaluation (~12 live tensors of rows x components x

@@ -1,0 +1,177 @@
+"""GPU tests (-m gpu) of the fused reverse sweep ``stpde_jet_backward``.
+
+Checker: the jets re-evaluated with differentiable torch ops in float64 (space_time_pde_b200/_torch_jets.py, itself pinned
+against the reference algorithm's autograd in tests/test_gpu_parity.py::test_training_step_gradients and, on CPU, in
+tests/test_host_logic.py) differentiated by torch.autograd for the same cotangents (gy, gjets).
+Tolerance: rel-L-infinity per gradient tensor 5e-5 in the split-precision mode (the gradient is a sum over ~10^4 rows of
+products that each carry the 2^-22 operand rounding, and tiny adjoints sit in the subnormal range of the lo plane), 5e-2 in the single-pass fp16 mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import space_time_pde_b200 as sp
+from space_time_pde_b200 import _torch_jets, jets
+from space_time_pde_b200.equations import JetSpec
+from tests.helpers import rel_linf
+
+pytestmark = pytest.mark.gpu
+BWD_TOLS = {"fp32": 5e-5, "fp16x3": 5e-5, "fp16": 5e-2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need CUDA (the hot path has no CPU fallback)"
+    return torch.device("cuda:0")
+
+
+def make_decoder(gen, d, c, o, nf, dev):
+    widths = [16 * nf, 8 * nf, 4 * nf, 2 * nf, nf, o]
+    D = d + c
+    Ws, bs = [], []
+    for l, w in enumerate(widths):
+        fan_in = D if l == 0 else widths[l - 1] + (D if l < len(widths) - 1 else 0)
+        bound = 1.0 / np.sqrt(fan_in)
+        Ws.append(((torch.rand(w, fan_in, generator=gen) * 2 - 1) * bound).to(dev))
+        bs.append(((torch.rand(w, generator=gen) * 2 - 1) * bound).to(dev))
+    return Ws, bs
+
+
+def reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj):
+    g64 = grid.double().requires_grad_(True)
+    W64 = [w.double().requires_grad_(True) for w in Ws]
+    b64 = [b.double().requires_grad_(True) for b in bs]
+    beta_t = torch.tensor(beta, dtype=torch.float64, device=grid.device)
+    grads = None
+    p = q.shape[1]
+    step = 512                                           # bounded autograd tape
+    for s in range(0, p, step):
+        sl = slice(s, min(p, s + step))
+        y, j = _torch_jets.query_jets(g64, q[:, sl].double(), lo.to(grid.device), hi.to(grid.device), W64, b64, act, beta_t, spec)
+        loss = (y * gy[:, sl].double()).sum()
+        if j is not None:
+            loss = loss + (j * gj[:, :, sl].double()).sum()
+        gs = torch.autograd.grad(loss, [g64] + W64 + b64, allow_unused=True)
+        gs = [torch.zeros_like(t) if g is None else g for g, t in zip(gs, [g64] + W64 + b64)]
+        grads = gs if grads is None else [a + b for a, b in zip(grads, gs)]
+    n = len(Ws)
+    return grads[0], grads[1:1 + n], grads[1 + n:]
+
+
+def run_case(dev, d, gshape, c, o, nf, act, first, second, p, precision, seed=0, beta=1.0, gscale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    Ws, bs = make_decoder(gen, d, c, o, nf, dev)
+    grid = (torch.randn(1, *gshape, c, generator=gen) * 0.5).to(dev)
+    q = (torch.rand(1, p, d, generator=gen) * (1 - 2e-6) + 1e-6).to(dev)
+    spec = JetSpec(tuple(first), tuple(second))
+    gy = (torch.randn(1, p, o, generator=gen) * gscale).to(dev)
+    gj = (torch.randn(max(spec.n_jet, 1), 1, p, o, generator=gen) * gscale * 0.05).to(dev) if spec.n_jet else None
+    lo, hi = jets.bounds_tensors(0., 1., d, dev)
+    ggrid, gW, gB = jets.raw_backward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, gy, gj)
+    torch.cuda.synchronize()
+    rgrid, rW, rB = reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj)
+    errs = {"grid": rel_linf(ggrid.cpu().numpy(), rgrid.cpu().numpy())}
+    for l in range(len(Ws)):
+        kh = 0 if l == 0 else Ws[l - 1].shape[0]
+        a, b = gW[l].cpu().numpy(), rW[l].cpu().numpy()
+        den = np.abs(b).max()
+        if kh:
+            errs[f"W{l}.act"] = float(np.abs(a[:, :kh] - b[:, :kh]).max() / den)
+        if l < len(Ws) - 1:
+            errs[f"W{l}.xrel"] = float(np.abs(a[:, kh:kh + d] - b[:, kh:kh + d]).max() / den)
+            errs[f"W{l}.lat"] = float(np.abs(a[:, kh + d:] - b[:, kh + d:]).max() / den)
+        errs[f"b{l}"] = rel_linf(gB[l].cpu().numpy(), rB[l].cpu().numpy())
+    print(f"bwd {act} d={d} nf={nf} K={1 + len(first) + len(second)} {precision}: " +
+          " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    return errs
+
+
+RB2 = ((0, 1, 2), ((1, 1), (2, 2)))
+PRECS = [p for p in os.environ.get("STPDE_TEST_PRECISIONS", "fp16x3,fp16").split(",") if p in ("fp16x3", "fp16")]
+
+
+@pytest.mark.parametrize("precision", PRECS)
+@pytest.mark.parametrize("act", ["softplus", "tanh", "swish", "elu"])
+def test_backward_rb2_spec_smooth_activations(act, precision, dev):
+    errs = run_case(dev, 3, (3, 4, 5), 16, 4, 8, act, *RB2, p=2048, precision=precision, seed=3, beta=1.3)
+    assert max(errs.values()) < BWD_TOLS[precision], errs
+
+
+@pytest.mark.parametrize("act", ["relu", "leakyrelu"])
+def test_backward_kinked_activations(act, dev):
+    # sigma'' = 0: only the value / first-order paths carry gradient; a pre-activation within rounding distance of 0
+    # flips sigma' at isolated rows, so the gate is looser (same convention as the forward tests)
+    errs = run_case(dev, 3, (3, 4, 5), 16, 4, 8, act, *RB2, p=2048, precision="fp16x3", seed=4)
+    assert max(errs.values()) < 2e-3, errs
+
+
+@pytest.mark.parametrize("case", [
+    (1, (9,), 8, 2, 8, (0,), ((0, 0),)),                         # d = 1, K = 3 (80-row tiles)
+    (2, (5, 6), 8, 3, 8, (0, 1), ((0, 1),)),                     # d = 2, mixed partial, K = 4
+    (3, (3, 4, 5), 16, 4, 8, (), ()),                            # values only, K = 1
+    (3, (3, 4, 5), 16, 4, 8, (0, 1, 2), ()),                     # gradient only, K = 4
+    (3, (3, 4, 5), 16, 4, 8, (0, 1, 2), tuple((a, b) for a in range(3) for b in range(a, 3))),   # full Hessian, K = 10
+    (4, (3, 3, 3, 3), 8, 4, 8, (0, 1, 2, 3), ((0, 0), (1, 1), (2, 2))),                           # d = 4, K = 8
+])
+def test_backward_dims_and_jet_specs(case, dev):
+    d, gshape, c, o, nf, first, second = case
+    errs = run_case(dev, d, gshape, c, o, nf, "softplus", first, second, p=1024, precision="fp16x3", seed=5)
+    assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
+
+
+@pytest.mark.parametrize("nf", [32, 64])
+def test_backward_wide_decoders(nf, dev):
+    # several 256-feature tiles per layer, 256-wide wgrad N tiles, multiple K slices
+    errs = run_case(dev, 3, (4, 6, 6), 32, 4, nf, "softplus", *RB2, p=1024, precision="fp16x3", seed=6)
+    assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
+
+
+def test_backward_tiny_cotangents_are_rescaled(dev):
+    # mean-reduced losses over 10^6 points give |gy| ~ 1e-7: the adjoint scale keeps them inside the fp16 planes
+    errs = run_case(dev, 3, (3, 4, 5), 16, 4, 8, "softplus", *RB2, p=1024, precision="fp16x3", seed=7, gscale=1e-7)
+    assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
+
+
+def test_backward_multi_chunk_matches_single_chunk(dev, monkeypatch):
+    errs1 = run_case(dev, 3, (3, 4, 5), 16, 4, 8, "tanh", *RB2, p=3000, precision="fp16x3", seed=8)
+    jets.release_workspaces()
+    monkeypatch.setenv("STPDE_WORKSPACE_MB", "64")          # forces several chunks (and a ragged last one)
+    errs2 = run_case(dev, 3, (3, 4, 5), 16, 4, 8, "tanh", *RB2, p=3000, precision="fp16x3", seed=8)
+    jets.release_workspaces()
+    assert max(errs1.values()) < BWD_TOLS["fp16x3"], errs1
+    assert max(errs2.values()) < BWD_TOLS["fp16x3"], errs2
+
+
+def test_training_step_fused_vs_torch_route(dev, monkeypatch):
+    """PDELayer + loss.backward(): the fused CUDA backward against the autograd re-evaluation on the same inputs."""
+    torch.manual_seed(0)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=16, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid0 = (torch.randn(2, 4, 6, 5, 16) * 0.5).to(dev)
+    q = torch.rand(2, 1500, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+
+    def grads(route):
+        monkeypatch.setenv("STPDE_BACKWARD", route)
+        grid = grid0.clone().requires_grad_(True)
+        model.zero_grad()
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        y, res = layer(q)
+        loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+        loss.backward()
+        return [grid.grad.clone()] + [p.grad.clone() for p in model.parameters()]
+
+    fused, ref = grads("fused"), grads("torch")
+    for i, (a, b) in enumerate(zip(fused, ref)):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4, i
+
+
+def test_backward_fallback_routes(dev):
+    """Gradients w.r.t. the query points still work (torch route), and so does a decoder the kernel does not cover."""
+    torch.manual_seed(1)
+    model = sp.ImNet(dim=3, in_features=8, out_features=2, nf=8, activation=sp.NONLINEARITIES["tanh"]).to(dev)
+    grid = (torch.randn(1, 3, 4, 5, 8) * 0.5).to(dev)
+    q = torch.rand(1, 64, 3, device=dev).requires_grad_(True)
+    y = sp.query_local_implicit_grid(model, grid, q, 0., 1.)
+    y.sum().backward()
+    assert q.grad is not None and torch.isfinite(q.grad).all()

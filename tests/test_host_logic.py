@@ -56,7 +56,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libstpde.so does not export {name}"
     assert set(_lib.EXPORTS) == declared
-    assert lib.stpde_version() == 100
+    assert lib.stpde_version() == 200
     assert lib.stpde_desc_size() == ctypes.sizeof(_lib.StpdeDesc)
 
 
