@@ -126,6 +126,15 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms of 1024 B
@@ -691,11 +700,17 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         // contraction (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with
         // the saved z planes and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the
         // closed-form layer 0 (nothing below it: only the parameter adjoints are accumulated).
+        // Rows are processed in steps of H (4 or 2): the z operands of the next half block are in flight while the
+        // current one is evaluated (the dependent vertex gather of MODE 3 would otherwise serialise every row).
+        constexpr int H = (MODE == kModeBwd0 || KC <= 3) ? 4 : 2;  // rows per step (register budget: 96 per thread)
+        constexpr int PC = (MODE == kModeBwd) ? KC : 1;            // prefetched values per row
+        constexpr bool kPrefetch = (MODE == kModeBwd0) || KC <= 8;
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
         const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
         const int64_t plane = (int64_t)args.rows * args.ld_out;
         const int64_t zplane = (int64_t)args.rows * args.ldz;
+        const int n_first = spec.n_first;
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
@@ -705,102 +720,174 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             const int g = f0 + quarter * 32 + lane;
             const bool g_store = g < args.n_store;
             const bool g_ok = g < args.n_feat;
-            float gx[kMaxDim];
+            float G[kMaxDim], A[KC];                                // per-tile partial sums of the coordinate-column adjoint
 #pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) gx[k] = 0.f;
-            float wx[kMaxDim];                                      // MODE 3: layer-0 coordinate columns of this feature
+            for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) A[c] = 0.f;
+            float wx[kMaxDim], cf[KC];                              // MODE 3: layer-0 coordinate columns / jet coefficients
 #pragma unroll
             for (int k = 0; k < kMaxDim; ++k)
                 wx[k] = (MODE == kModeBwd0 && k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                float wa = 1.f, wb = 1.f;
+                if constexpr (MODE == kModeBwd0) {
+#pragma unroll
+                    for (int k = 0; k < kMaxDim; ++k) {
+                        if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
+                        if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
+                        if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
+                    }
+                }
+                cf[c] = wa * wb;
+            }
+            // operands of one half block: MODE 2 the saved pre-activations, MODE 3 the recomputed z0 of layer 0
+            auto fetch = [&](int row0, float (&pz)[PC][H]) {
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const int rc = min(row0 + j, args.rows - 1);
+                    if constexpr (MODE == kModeBwd) {
+#pragma unroll
+                        for (int c = 0; c < KC; ++c)
+                            pz[c][j] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
+                    } else {
+                        float z0 = g_ok ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + rc) * args.ncat + args.cat_off + g) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < kMaxDim; ++k)
+                            if (k < args.dim) z0 = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + rc), z0);
+                        pz[0][j] = z0;
+                    }
+                }
+            };
+            float zc[PC][H], zn[PC][H];
+            if (kPrefetch && sub < NRB) fetch(r0 + sub * 8, zc);
             mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
             float amax = 0.f;
 #pragma unroll 1
             for (int rb = sub; rb < NRB; rb += kEpiPQ) {
-                uint32_t v[KC][8];
 #pragma unroll
-                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
-                tmem_wait_ld();
+                for (int h = 0; h < 8 / H; ++h) {
+                    const int rbase = r0 + rb * 8 + h * H;
+                    uint32_t v[KC][H];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + rb * 8 + i;
-                    const bool r_ok = r < args.rows;
-                    const int rc = min(r, args.rows - 1);
-                    const int vrow = __ldg(args.vtx + rc);
-                    float xr[kMaxDim];
-#pragma unroll
-                    for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
-                    float ab[KC];
-#pragma unroll
-                    for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][i]) * scale : 0.f;
-                    float z0b;
-                    if constexpr (MODE == kModeBwd) {
-                        float z[KC], zb[KC];
-#pragma unroll
-                        for (int c = 0; c < KC; ++c)
-                            z[c] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
-                        float s1, s2, s3;
-                        act_d123_fast(args.act, args.beta, z[0], s1, s2, s3);
-                        jet_act_backward<KC>(spec, s1, s2, s3, z, ab, zb);
-                        z0b = zb[0];
-#pragma unroll
-                        for (int c = 1; c < KC; ++c)
-#pragma unroll
-                            for (int k = 0; k < kMaxDim; ++k)
-                                if (spec.kind[c] == 1 && spec.dir[c] == k) gx[k] += zb[c];
-                        if (g_store && r_ok) {
-                            const int64_t off = (int64_t)r * args.ld_out + g;
-                            __half* ph = args.out_hi + off;
-                            __half* pl = args.out_lo + off;
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) {
-                                const float xs = zb[c];
-                                amax = fmaxf(amax, fabsf(xs));
-                                const __half hi = __float2half_rn(xs);
-                                *ph = hi;
-                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
-                                ph += plane; pl += plane;
-                            }
-                        }
-                    } else {
-                        // layer 0: a_c = sigma^(order_c)(z0) * coef_c, coef = 1 | W0x[dir] | W0x[dir_a] * W0x[dir_b]
-                        float z0 = g_ok ? __ldg(args.Vb + (int64_t)vrow * args.ncat + args.cat_off + g) : 0.f;
-#pragma unroll
-                        for (int k = 0; k < kMaxDim; ++k) z0 = fmaf(wx[k], xr[k], z0);
-                        float s1, s2, s3;
-                        act_d123_fast(args.act, args.beta, z0, s1, s2, s3);
-                        z0b = 0.f;
-#pragma unroll
-                        for (int c = 0; c < KC; ++c) {
-                            float wa = 1.f, wb = 1.f;
-#pragma unroll
-                            for (int k = 0; k < kMaxDim; ++k) {
-                                if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
-                                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
-                                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
-                            }
-                            const float sd = spec.kind[c] == 0 ? s1 : spec.kind[c] == 1 ? s2 : s3;   // d a_c / d z0
-                            const float sl = spec.kind[c] == 0 ? 0.f : spec.kind[c] == 1 ? s1 : s2;  // d a_c / d coef_c
-                            z0b = fmaf(ab[c] * sd, wa * wb, z0b);
-                            const float t = ab[c] * sl;
-#pragma unroll
-                            for (int k = 0; k < kMaxDim; ++k) {
-                                if (spec.kind[c] == 1 && k == spec.dir[c]) gx[k] += t;
-                                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) gx[k] = fmaf(t, wb, gx[k]);
-                                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) gx[k] = fmaf(t, wa, gx[k]);
-                            }
-                        }
+                    for (int c = 0; c < KC; ++c) {
+                        if constexpr (H == 4) tmem_ld_x4(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
+                        else tmem_ld_x2(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
                     }
+                    if constexpr (kPrefetch) {
+                        if (h + 1 < 8 / H) fetch(rbase + H, zn);
+                        else if (rb + kEpiPQ < NRB) fetch(r0 + (rb + kEpiPQ) * 8, zn);
+                    } else {
+                        fetch(rbase, zc);
+                    }
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < kMaxDim; ++k) gx[k] = fmaf(z0b, xr[k], gx[k]);
-                    if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+                    for (int j = 0; j < H; ++j) {
+                        const int r = rbase + j;
+                        const bool r_ok = r < args.rows;
+                        const int rc = min(r, args.rows - 1);
+                        const int vrow = __ldg(args.vtx + rc);        // L1-resident: shared by every feature of the tile
+                        float xr[kMaxDim];
+#pragma unroll
+                        for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
+                        float ab[KC];
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
+                        float s1, s2, s3, z0b;
+                        act_d123_fast(args.act, args.beta, zc[0][j], s1, s2, s3);
+                        if constexpr (MODE == kModeBwd) {
+                            float zb[KC], cross[STPDE_MAX_FIRST];
+#pragma unroll
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+                            float u = 0.f, w3 = 0.f;
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) {
+                                u = fmaf(ab[c], zc[c][j], u);
+                                zb[c] = s1 * ab[c];
+                                if (c > n_first) {                 // second order (warp-uniform): parents za, zp
+                                    float za = 0.f, zp = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                        if (1 + k < KC) {
+                                            za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
+                                            zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
+                                        }
+                                    }
+                                    w3 = fmaf(ab[c] * za, zp, w3);
+#pragma unroll
+                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                        if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
+                                }
+                            }
+                            z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
+                            zb[0] = z0b;
+#pragma unroll
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) A[c] += zb[c];
+                            if (g_store && r_ok) {
+                                const int64_t off = (int64_t)r * args.ld_out + g;
+                                __half* ph = args.out_hi + off;
+                                __half* pl = args.out_lo + off;
+#pragma unroll
+                                for (int c = 0; c < KC; ++c) {
+                                    const float xs = zb[c];
+                                    amax = fmaxf(amax, fabsf(xs));
+                                    const __half hi = __float2half_rn(xs);
+                                    *ph = hi;
+                                    if (three) *pl = __float2half_rn(xs - __half2float(hi));
+                                    ph += plane; pl += plane;
+                                }
+                            }
+                        } else {
+                            // layer 0: a_c = sigma^(order_c)(z0) * cf_c
+                            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) {
+                                const float pc = ab[c] * cf[c];
+                                if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
+                                else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
+                            }
+                            z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
+                        }
+#pragma unroll
+                        for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
+                        if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+                    }
+                    if constexpr (kPrefetch) {
+#pragma unroll
+                        for (int c = 0; c < PC; ++c)
+#pragma unroll
+                            for (int j = 0; j < H; ++j) zc[c][j] = zn[c][j];
+                    }
                 }
             }
             if (g_ok) {
+                // fold the per-component sums into the coordinate columns (once per tile)
+#pragma unroll
+                for (int c = 1; c < KC; ++c) {
+#pragma unroll
+                    for (int k = 0; k < kMaxDim; ++k) {
+                        if (spec.kind[c] == 1 && k == spec.dir[c]) G[k] += A[c];
+                        if constexpr (MODE == kModeBwd0) {
+                            if (spec.kind[c] == 2) {
+                                const int da = spec.dir[spec.pa[c]], db = spec.dir[spec.pb[c]];
+                                float wda = 0.f, wdb = 0.f;
+#pragma unroll
+                                for (int kk = 0; kk < kMaxDim; ++kk) { if (kk == da) wda = wx[kk]; if (kk == db) wdb = wx[kk]; }
+                                if (k == da) G[k] = fmaf(A[c], wdb, G[k]);
+                                if (k == db) G[k] = fmaf(A[c], wda, G[k]);
+                            }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < kMaxDim; ++k)
-                    if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, gx[k]);
+                    if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
             }
             if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
             tc_fence_before();

@@ -1,0 +1,30 @@
+"""One training step (forward + residuals + L1 losses + fused reverse sweep) at BASELINE config[1] shapes with fewer
+points, for ncu captures of the reverse-mode kernels."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import space_time_pde_b200 as sp
+from space_time_pde_b200 import jets
+
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
+npts = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+jets.set_default_precision(precision)
+dev = torch.device("cuda:0")
+model = bench.make_model(dev)
+grid, q = bench.synthetic_inputs(1234, dev, npts)
+grid.requires_grad_(True)
+layer = sp.get_rb2_pde_layer(**bench.RB2)
+layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+for _ in range(steps):
+    model.zero_grad()
+    grid.grad = None
+    y, res = layer(q)
+    loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+    loss.backward()
+torch.cuda.synchronize()
+print("ok", float(loss), float(grid.grad.abs().max()))
