@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("STPDE_PRECISION", "fp16x3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-chunk", type=int, default=16384, help="query points per forward/backward chunk of the training leg")
+    ap.add_argument("--train-workspace-mb", type=int, default=40960, help="workspace budget of the training leg (stash of one chunk)")
     ap.add_argument("--train-steps", type=int, default=1,
                     help="timed training steps (forward + residuals + loss + fused backward [+ all-reduce]); 0 skips the leg")
     args = ap.parse_args()
@@ -338,14 +340,26 @@ def main():
         reducer = StepReducer(params)
         layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid_t, pts, 0., 1.))
 
+        # Points are independent, so the step walks the batch in chunks that fit the training stash (the forward of
+        # a chunk leaves its operand planes in the workspace and the chunk's backward reuses them: no recompute);
+        # gradients accumulate in .grad across chunks exactly as one big backward would.
+        os.environ["STPDE_WORKSPACE_MB"] = str(args.train_workspace_mb)
+        jets.release_workspaces()
+        tchunk = args.train_chunk
+
         def train_step():
             for p_ in params:
                 p_.grad = None
-            y, res = layer(q, return_residue=True)
-            reg = y.abs().sum()
-            pde = torch.stack(list(res.values())).abs().sum()
-            (reg / (world * y.numel()) + 0.0125 * pde / (world * 4 * NPTS)).backward()
-            return reducer.reduce({"reg": reg, "pde": pde}, {"reg": y.numel(), "pde": 4 * NPTS})
+            reg_sum = torch.zeros((), device=device)
+            pde_sum = torch.zeros((), device=device)
+            for s0 in range(0, NPTS, tchunk):
+                y, res = layer(q[:, s0:s0 + tchunk], return_residue=True)
+                reg = y.abs().sum()
+                pde = torch.stack(list(res.values())).abs().sum()
+                (reg / (world * 4 * NPTS) + 0.0125 * pde / (world * 4 * NPTS)).backward()
+                reg_sum += reg.detach()
+                pde_sum += pde.detach()
+            return reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": 4 * NPTS, "pde": 4 * NPTS})
 
         train_step()
         barrier()
@@ -366,7 +380,9 @@ def main():
         # algorithmic FLOPs of a training step = 3 x the forward contractions (forward, dgrad, wgrad); the recompute
         # of the forward inside the backward is overhead, not counted
         train = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
-                 "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients)"
+                 "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
+                 "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients), "
+                         "chunks of the batch with the forward planes kept for the backward (no recompute)"
                          + (" + one NCCL all-reduce of the flat gradient buffer" if world > 1 else ""),
                  "algorithmic_tflops": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12,
                  "frac_of_peak": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12 / peaks["tflops"],
@@ -375,6 +391,7 @@ def main():
                  "gpu_launches_per_step": int(sum(v[1] for v in prof_t.values()) / args.train_steps)}
         for p_ in params:
             p_.grad = None
+        jets.release_workspaces()
         layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
 
     if world > 1:

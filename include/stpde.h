@@ -172,11 +172,30 @@ int stpde_jet_forward(const stpde_desc_t *desc, const float *grid, const int64_t
  * adjoints).
  */
 size_t stpde_backward_workspace_bytes(const stpde_desc_t *desc);
+/* points per chunk the reverse-mode layout gets out of a workspace of that size (0: too small / unsupported) */
+int64_t stpde_backward_chunk_points(const stpde_desc_t *desc, size_t workspace_bytes);
+/*
+ * reuse_forward = 1: the workspace still holds the planes of a stpde_jet_forward_train call with the SAME
+ * descriptor, inputs and workspace (nothing else may have written to it in between); the recompute is skipped.
+ */
 int stpde_jet_backward(const stpde_desc_t *desc, const float *grid, const int64_t *grid_strides,
                        const float *q, const int64_t *q_strides, const float *const *W,
                        const float *const *B, const float *gy, const float *gjets, float *const *gW,
                        float *const *gB, float *ggrid, void *workspace, size_t workspace_bytes,
-                       int32_t *status, void *stream);
+                       int32_t reuse_forward, int32_t *status, void *stream);
+
+/*
+ * Training forward: same outputs as stpde_jet_forward (tensor-core arithmetic), but every operand plane and
+ * pre-activation of the batch is left in the workspace (reverse-mode layout, stpde_backward_workspace_bytes) so that
+ * stpde_jet_backward(reuse_forward = 1) does not have to recompute the forward.  The whole batch must fit ONE chunk
+ * (stpde_backward_chunk_points(desc, workspace_bytes) >= batch * npts), otherwise STPDE_ENOMEM: use
+ * stpde_jet_forward and let the backward recompute chunk by chunk.  This is the path a training step of the
+ * reference's size takes (experiments/rb2d/train.py: a few thousand query points per step).
+ */
+int stpde_jet_forward_train(const stpde_desc_t *desc, const float *grid, const int64_t *grid_strides,
+                            const float *q, const int64_t *q_strides, const float *const *W,
+                            const float *const *B, float *y, float *jets, void *workspace,
+                            size_t workspace_bytes, int32_t *status, void *stream);
 
 /*
  * Same computation with HOST buffers (grid, q, weights, y, jets all in host memory; grid and q

@@ -47,7 +47,8 @@ class StpdeDesc(ctypes.Structure):
 
 EXPORTS = ["stpde_version", "stpde_last_error", "stpde_desc_size", "stpde_device_sm_count", "stpde_workspace_bytes",
            "stpde_interp_coefficients", "stpde_interp", "stpde_jet_forward", "stpde_jet_forward_host",
-           "stpde_backward_workspace_bytes", "stpde_jet_backward",
+           "stpde_backward_workspace_bytes", "stpde_backward_chunk_points", "stpde_jet_backward",
+           "stpde_jet_forward_train",
            "stpde_residuals", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
 
 
@@ -123,7 +124,11 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.stpde_jet_backward.restype = c_int
     lib.stpde_jet_backward.argtypes = [descp, c_void_p, i64p, c_void_p, i64p, ctypes.POINTER(c_void_p),
                                        ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
-                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, i32, c_void_p, c_void_p]
+    lib.stpde_backward_chunk_points.restype = ctypes.c_int64
+    lib.stpde_backward_chunk_points.argtypes = [descp, c_size_t]
+    lib.stpde_jet_forward_train.restype = c_int
+    lib.stpde_jet_forward_train.argtypes = lib.stpde_jet_forward.argtypes
     lib.stpde_jet_forward_host.restype = c_int
     lib.stpde_jet_forward_host.argtypes = [descp, c_void_p, c_void_p, ctypes.POINTER(c_void_p),
                                            ctypes.POINTER(c_void_p), c_void_p, c_void_p]
@@ -160,11 +165,12 @@ def load() -> ctypes.CDLL:
 def profile_read():
     """{slot name: (milliseconds, launches)} since the previous read (synchronises the device)."""
     lib = load()
-    n = 16
+    n = 32
     ms = (ctypes.c_double * n)()
     cnt = (ctypes.c_int64 * n)()
     lib.stpde_profile_read(ms, cnt, n)
-    return {lib.stpde_profile_slot_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+    return {lib.stpde_profile_slot_name(i).decode(): (ms[i], cnt[i]) for i in range(n)
+            if lib.stpde_profile_slot_name(i)}
 
 
 def check(rc: int) -> None:

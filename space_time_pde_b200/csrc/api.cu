@@ -309,22 +309,40 @@ static int64_t default_bwd_chunk_points(const Plan& P) {
 // latent grid.  Per chunk of points: recompute the forward keeping every operand plane, then blend_backward ->
 // (wgrad, dgrad) per hidden layer on the tensor cores; the per-vertex adjoint gVb is folded into the latent-column
 // weights, the biases and the grid once at the end.
-static int run_backward(const Plan& P, const stpde_desc_t* d, const float* grid, const float* q, const float* const* W,
-                        const float* const* B, const float* gy, const float* gjets, float* const* gW, float* const* gB,
-                        float* ggrid, char* ws, size_t ws_bytes, int* status, cudaStream_t st) {
-    const int dim = d->dim, kc = P.spec.kc, L = P.n_layers - 1;
-    for (int l = 0; l < P.n_layers; ++l) {
-        CUDA_TRY(cudaMemsetAsync(gW[l], 0, (size_t)P.widths[l] * P.in_features[l] * sizeof(float), st));
-        CUDA_TRY(cudaMemsetAsync(gB[l], 0, (size_t)P.widths[l] * sizeof(float), st));
-    }
-    if (ggrid) CUDA_TRY(cudaMemsetAsync(ggrid, 0, (size_t)P.nvert_total * d->channels * sizeof(float), st));
-    if (P.total_pts == 0) return STPDE_OK;
-    if (ws_bytes < P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128))
-        return fail(STPDE_ENOMEM, "workspace %zu B < minimum %zu B", ws_bytes, P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128));
+// points per chunk of the reverse-mode layout for a workspace of ws_bytes (0: too small)
+static int64_t bwd_chunk_points(const Plan& P, size_t ws_bytes) {
+    if (ws_bytes < P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128)) return 0;
     int64_t pc = (int64_t)((ws_bytes - P.bwd_fixed_bytes - 64 * 1024) / P.bwd_per_point_bytes) / 128 * 128;
     int64_t need = (P.total_pts + 127) / 128 * 128;
     if (pc > need) pc = need;
     if (pc > (1 << 22)) pc = 1 << 22;
+    return pc;
+}
+
+enum { kBwdFull = 0, kBwdForwardOnly = 1, kBwdReuse = 2 };
+
+// mode kBwdFull        : recompute the forward per chunk, then the reverse sweep
+//      kBwdForwardOnly : training forward (stpde_jet_forward_train): the single chunk's planes stay in the workspace
+//      kBwdReuse       : reverse sweep on the planes a kBwdForwardOnly call left in the SAME workspace
+static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const float* grid, const float* q,
+                        const float* const* W, const float* const* B, const float* gy, const float* gjets,
+                        float* const* gW, float* const* gB, float* ggrid, float* y, float* jets, char* ws,
+                        size_t ws_bytes, int* status, cudaStream_t st) {
+    const int dim = d->dim, kc = P.spec.kc, L = P.n_layers - 1;
+    if (mode != kBwdForwardOnly) {
+        for (int l = 0; l < P.n_layers; ++l) {
+            CUDA_TRY(cudaMemsetAsync(gW[l], 0, (size_t)P.widths[l] * P.in_features[l] * sizeof(float), st));
+            CUDA_TRY(cudaMemsetAsync(gB[l], 0, (size_t)P.widths[l] * sizeof(float), st));
+        }
+        if (ggrid) CUDA_TRY(cudaMemsetAsync(ggrid, 0, (size_t)P.nvert_total * d->channels * sizeof(float), st));
+    }
+    if (P.total_pts == 0) return STPDE_OK;
+    int64_t pc = bwd_chunk_points(P, ws_bytes);
+    if (pc == 0)
+        return fail(STPDE_ENOMEM, "workspace %zu B < minimum %zu B", ws_bytes, P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, 128));
+    if (mode != kBwdFull && pc < P.total_pts)
+        return fail(STPDE_ENOMEM, "the training forward keeps ONE chunk: %lld points do not fit the workspace (%lld)",
+                    (long long)P.total_pts, (long long)pc);
     const int64_t rows = pc * P.ncorner;
     if (rows * (int64_t)P.np64[0] * kc >= (int64_t)1 << 40 || rows >= ((int64_t)1 << 31))
         return fail(STPDE_EUNSUPPORTED, "chunk too large");
@@ -369,11 +387,13 @@ static int run_backward(const Plan& P, const stpde_desc_t* d, const float* grid,
     }
     launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
     CUDA_TRY(cudaMemsetAsync(g_vb, 0, (size_t)P.nvert_total * P.ncat * sizeof(float), st));
-    // reserved[0] = headroom bits below the default adjoint scale (the binding retries with more headroom when the
-    // range flag comes back)
-    int target_exp = 10 - d->reserved[0];
-    target_exp = target_exp > 14 ? 14 : (target_exp < -40 ? -40 : target_exp);
-    launch_grad_scale(P.spec, P.geom, gy, kc > 1 ? gjets : nullptr, P.total_pts * P.O, maxes, scale, target_exp, st);
+    if (mode != kBwdForwardOnly) {
+        // reserved[0] = headroom bits below the default adjoint scale (the binding retries with more headroom when
+        // the range flag comes back)
+        int target_exp = 10 - d->reserved[0];
+        target_exp = target_exp > 14 ? 14 : (target_exp < -40 ? -40 : target_exp);
+        launch_grad_scale(P.spec, P.geom, gy, kc > 1 ? gjets : nullptr, P.total_pts * P.O, maxes, scale, target_exp, st);
+    }
     prof_end(kSlotSetup, st, P.n_layers + 4);
 
     TcBwdContext tc;
@@ -383,13 +403,21 @@ static int run_backward(const Plan& P, const stpde_desc_t* d, const float* grid,
 
     const TcBwdLayer& TL = tc.layer[P.n_layers - 2];
     for (int64_t p0 = 0; p0 < P.total_pts; p0 += pc) {
-        {
-            ProfScope ps(kSlotPrep, st);
-            launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
+        if (mode != kBwdReuse) {
+            {
+                ProfScope ps(kSlotPrep, st);
+                launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
+            }
+            rc = tc_bwd_forward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, Wx, act_last,
+                                      np_last, st);
+            if (rc) return fail(rc, "%s", tc_last_error());
         }
-        rc = tc_bwd_forward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, Wx, act_last,
-                                  np_last, st);
-        if (rc) return fail(rc, "%s", tc_last_error());
+        if (mode == kBwdForwardOnly) {
+            ProfScope ps(kSlotFinal, st);
+            launch_final_blend(P.spec, dim, cb.rows, cb.pc, P.total_pts, p0, P.kp[L], P.O, act_last,
+                               (const float*)(ws + P.off_wh[L]), B[L], cb, y, jets, st);
+            break;
+        }
         {
             BlendBwdArgs a;
             memset(&a, 0, sizeof(a));
@@ -413,7 +441,7 @@ static int run_backward(const Plan& P, const stpde_desc_t* d, const float* grid,
                                    gW, g_vb, st);
         if (rc) return fail(rc, "%s", tc_last_error());
     }
-    {
+    if (mode != kBwdForwardOnly) {
         ProfScope ps(kSlotBwdVertex, st, 3 + 2 * P.n_layers);
         VertexBwdArgs v;
         memset(&v, 0, sizeof(v));
@@ -499,10 +527,29 @@ size_t stpde_backward_workspace_bytes(const stpde_desc_t* desc) {
     return P.bwd_fixed_bytes + bwd_chunk_region_bytes(P, default_bwd_chunk_points(P));
 }
 
+int64_t stpde_backward_chunk_points(const stpde_desc_t* desc, size_t workspace_bytes) {
+    Plan P;
+    if (make_plan(P, desc, nullptr, nullptr) != STPDE_OK || P.n_layers < 3) return 0;
+    return bwd_chunk_points(P, workspace_bytes);
+}
+
+int stpde_jet_forward_train(const stpde_desc_t* desc, const float* grid, const int64_t* grid_strides, const float* q,
+                            const int64_t* q_strides, const float* const* W, const float* const* B, float* y, float* jets,
+                            void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+    Plan P;
+    int rc = make_plan(P, desc, grid_strides, q_strides);
+    if (rc) return rc;
+    if (P.n_layers < 3) return fail(STPDE_EUNSUPPORTED, "the training forward needs at least 3 linear layers");
+    if (!grid || !q || !W || !B || !y || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
+    if (P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
+    return run_backward(kBwdForwardOnly, P, desc, grid, q, W, B, nullptr, nullptr, nullptr, nullptr, nullptr, y, jets,
+                        (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
+}
+
 int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_t* grid_strides, const float* q,
                        const int64_t* q_strides, const float* const* W, const float* const* B, const float* gy,
                        const float* gjets, float* const* gW, float* const* gB, float* ggrid, void* workspace,
-                       size_t workspace_bytes, int32_t* status, void* stream) {
+                       size_t workspace_bytes, int32_t reuse_forward, int32_t* status, void* stream) {
     Plan P;
     int rc = make_plan(P, desc, grid_strides, q_strides);
     if (rc) return rc;
@@ -511,8 +558,8 @@ int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_
     if (P.spec.kc > 1 && !gjets) return fail(STPDE_EINVAL, "gjets required when derivatives were requested");
     for (int l = 0; l < P.n_layers; ++l)
         if (!W[l] || !B[l] || !gW[l] || !gB[l]) return fail(STPDE_EINVAL, "null weight / gradient pointer for layer %d", l);
-    return run_backward(P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, (char*)workspace, workspace_bytes, status,
-                        (cudaStream_t)stream);
+    return run_backward(reuse_forward ? kBwdReuse : kBwdFull, P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, nullptr,
+                        nullptr, (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
 }
 
 int stpde_jet_forward_host(const stpde_desc_t* desc, const float* grid, const float* q, const float* const* W,

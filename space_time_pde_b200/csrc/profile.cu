@@ -17,7 +17,11 @@ std::vector<Pair> g_free;
 int64_t g_launches[kNumSlots] = {0};
 const char* kNames[kNumSlots] = {"setup", "prep_points", "layer0_jets", "gemm_layer1", "gemm_layer2", "gemm_layer3",
                                  "gemm_layer4", "gemm_layer5", "gemm_layer6", "gemm_layer7", "final_blend",
-                                 "residuals", "bwd_blend", "bwd_wgrad", "bwd_dgrad", "bwd_vertex"};
+                                 "residuals", "bwd_blend", "bwd_vertex", "", "",
+                                 "bwd_wgrad_layer1", "bwd_wgrad_layer2", "bwd_wgrad_layer3", "bwd_wgrad_layer4",
+                                 "bwd_wgrad_layer5", "bwd_wgrad_layer6", "bwd_wgrad_layer7", "",
+                                 "bwd_dgrad_layer1", "bwd_dgrad_layer2", "bwd_dgrad_layer3", "bwd_dgrad_layer4",
+                                 "bwd_dgrad_layer5", "bwd_dgrad_layer6", "bwd_dgrad_layer7", ""};
 }  // namespace
 
 void prof_begin(int slot, cudaStream_t st) {

@@ -13,10 +13,10 @@ enum ProfSlot {
     kSlotFinal = 10,    // last linear layer + blend
     kSlotResidual = 11, // residual programs
     kSlotBwdBlend = 12, // reverse: blend + last layer + last hidden activation
-    kSlotWgrad = 13,    // reverse: weight-gradient contractions
-    kSlotDgrad = 14,    // reverse: activation-gradient contractions + reverse jet activation
-    kSlotBwdVertex = 15,// reverse: per-vertex adjoint -> latent columns, biases, grid; final 1/S
-    kNumSlots = 16
+    kSlotBwdVertex = 13,// reverse: per-vertex adjoint -> latent columns, biases, grid; final 1/S
+    kSlotWgrad = 16,    // reverse: weight-gradient contraction of hidden layer l at kSlotWgrad + (l - 1)
+    kSlotDgrad = 24,    // reverse: activation-gradient contraction + reverse jet activation, kSlotDgrad + (l - 1)
+    kNumSlots = 32
 };
 
 void prof_begin(int slot, cudaStream_t st);

@@ -2,6 +2,7 @@
 #include "tc_bwd.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bwd_kernels.h"
@@ -148,6 +149,8 @@ static void base_args(tc::LayerArgs& a, const TcBwdContext& tc, int dim, int act
     a.xrel = cb.xrel;
     a.status = tc.status;
     a.fast_act = 1;
+    const char* w = getenv("STPDE_WAIT_NS");
+    a.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u;
 }
 
 int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
@@ -238,7 +241,7 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
     for (int l = tc.n_layers - 2; l >= 1; --l) {
         const TcBwdLayer& L = tc.layer[l];
         {
-            ProfScope ps(kSlotWgrad, st);
+            ProfScope ps(kSlotWgrad + l - 1, st);
             int rc = launch_wgrad(tc, L, gW[l], in_features[l], st);
             if (rc) return rc;
         }
@@ -256,7 +259,7 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         const int kh_below = l >= 2 ? tc.layer[l - 1].kh : 0;      // activation columns of layer l-1's weight
         a.g_wx = gW[l - 1] + kh_below;
         a.g_wx_ld = in_features[l - 1];
-        ProfScope ps(kSlotDgrad, st);
+        ProfScope ps(kSlotDgrad + l - 1, st);
         int rc;
         if (l >= 2) {
             a.z_in = tc.layer[l - 1].z;

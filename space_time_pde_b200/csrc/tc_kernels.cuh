@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Wait for a barrier phase.  try_wait carries a suspend-time hint so the warp SLEEPS in hardware until the
 // phase completes (a hot spin loop here steals issue slots from the single TMA / MMA issuing threads).
 // Bounded: a protocol bug must surface as a trapped kernel (error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, uint32_t hint_ns = 0x989680u) {
     uint32_t done = 0;
     unsigned long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* st
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "r"(bar), "r"(parity), "r"(hint_ns)
             : "memory");
         if (done) return;
         if ((spin & 63u) == 63u) {          // wall-clock bound (profilers / time slicing can stretch a wait a lot)
@@ -132,6 +132,9 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
 }
@@ -186,6 +189,7 @@ struct LayerArgs {
     float* g_vb;           // MODE 2/3: adjoint of Vb, [nvert][ncat] (atomics)
     float* g_wx;           // MODE 2/3: adjoint of the coordinate columns, &gW[0][kh], row stride g_wx_ld (atomics)
     int g_wx_ld;
+    uint32_t wait_ns;      // suspend-time hint of the mbarrier waits (pair kernel)
 };
 
 // kernel modes of tc_layer_pair_kernel
@@ -539,7 +543,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF;
             const int r0 = (t / n_ftiles) * NR + (int)rank * (NR / 2);
             for (int kb = 0; kb < kb_count; ++kb) {
-                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status, args.wait_ns);
                 const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);   // the leader's copy of the barrier
                 const uint32_t base = smem_u32(smem + stage * stage_bytes);
                 const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
@@ -569,11 +573,11 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             int it = 0;
             for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
                 const int buf = it & 1;
-                mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
+                mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status, args.wait_ns);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * N;
                 for (int kb = 0; kb < kb_count; ++kb) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
+                    mbar_wait(smem_u32(&full_bar[stage]), phase, args.status, args.wait_ns);
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + stage * stage_bytes);
                     const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
@@ -624,7 +628,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             }
             for (int kb = 0; kb < kb_count; ++kb, ++gcount) {
                 if ((gcount & 1u) == (uint32_t)set) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status, args.wait_ns);
                     uint8_t* a_tile = smem + stage * stage_bytes + (three ? 2 * kWBytes : kWBytes);
 #pragma unroll
                     for (int q = 0; q < kPerThread; ++q) {
@@ -762,7 +766,23 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             };
             float zc[PC][H], zn[PC][H];
             if (kPrefetch && sub < NRB) fetch(r0 + sub * 8, zc);
-            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
+            if constexpr (MODE == kModeBwd) {
+                // The z planes stream from HBM (no reuse): pull the lines of this warp's NEXT tile into L2 now, one
+                // 128-byte line (32 features of one row and component) per lane, so that the register prefetch above
+                // sees an L2 hit instead of the full DRAM latency once per step.
+                const int tn = t + n_pairs;
+                const int f0n = (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32;
+                if (tn < n_tiles && f0n < args.n_feat) {
+                    for (int rb = sub; rb < NRB; rb += kEpiPQ) {
+                        const int r0n = (tn / n_ftiles) * NR + rb * 8;
+                        for (int idx = lane; idx < KC * 8; idx += 32) {
+                            const int rn = min(r0n + (idx & 7), args.rows - 1);
+                            prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + f0n);
+                        }
+                    }
+                }
+            }
+            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status, args.wait_ns);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
             float amax = 0.f;
@@ -934,7 +954,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             }
             float zs[8];
             if (sub < NRB) load_skip(r0 + sub * 8, g, wx, zs);
-            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
+            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status, args.wait_ns);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
             float amax = 0.f;

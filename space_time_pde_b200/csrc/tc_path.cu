@@ -396,6 +396,7 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
         a.fast_act = tc.fast_act;
+        { const char* w = getenv("STPDE_WAIT_NS"); a.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u; }
         a.n0 = tc.n0;
         a.wx0p = tc.wx0p;
         a.coef0 = tc.coef0;

@@ -7,6 +7,7 @@
 from __future__ import annotations
 
 import ctypes
+import itertools
 import os
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -84,6 +85,31 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def release_workspaces() -> None:
     _workspaces.clear()
+    _stashes.clear()
+
+
+class _Stash:
+    """Workspace that holds the operand planes of the latest training forward on a device (reverse-mode layout).
+
+    ``token`` identifies the forward call whose planes are in ``ws``; a backward may skip its recompute only when
+    its own token is still the current one (any later training forward on the device replaces it)."""
+
+    def __init__(self, ws: torch.Tensor):
+        self.ws = ws
+        self.token = 0
+
+
+_stashes: Dict[torch.device, _Stash] = {}
+_stash_tokens = itertools.count(1)
+
+
+def _stash(device: torch.device, nbytes: int) -> _Stash:
+    st = _stashes.get(device)
+    if st is None or st.ws.numel() < nbytes:
+        _stashes.pop(device, None)
+        st = _Stash(torch.empty(nbytes, dtype=torch.uint8, device=device))
+        _stashes[device] = st
+    return st
 
 
 def bounds_tensors(xmin, xmax, dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -136,8 +162,12 @@ def _i64(values) -> ctypes.Array:
 
 def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
                 Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
-                spec: JetSpec, precision: str, check: bool = True):
-    """One C-ABI call per <=10-component sub-spec; returns y [b,p,o], jets [n_jet,b,p,o] or None."""
+                spec: JetSpec, precision: str, check: bool = True, stash_out: Optional[list] = None):
+    """One C-ABI call per <=10-component sub-spec; returns y [b,p,o], jets [n_jet,b,p,o] or None.
+
+    ``stash_out`` (a list) asks for the TRAINING forward (``stpde_jet_forward_train``): when the whole batch fits
+    one chunk of the reverse-mode workspace its operand planes are kept there and the stash token is appended to
+    the list, so that the backward of this call can skip the recompute."""
     if _test_backend is not None and not q.is_cuda:
         return _test_backend(grid, q, lo, hi, Ws, bs, act, act_param, spec)
     if not (grid.is_cuda and q.is_cuda):
@@ -161,7 +191,21 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
     gstr, qstr = _i64(grid.stride()), _i64(q.stride())
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
-        for sub in spec.split(_lib.MAX_COMPONENTS):
+        subs = spec.split(_lib.MAX_COMPONENTS)
+        if stash_out is not None and len(subs) == 1 and precision != "fp32" and len(Wc) >= 3 and b * p > 0:
+            desc = make_desc(grid, q, lo, hi, widths, act, act_param, spec, precision)
+            nbytes = lib.stpde_backward_workspace_bytes(ctypes.byref(desc))
+            if nbytes and lib.stpde_backward_chunk_points(ctypes.byref(desc), nbytes) >= b * p:
+                st = _stash(device, nbytes)
+                st.token = 0
+                rc = lib.stpde_jet_forward_train(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr,
+                                                 bptr, y.data_ptr(), jets.data_ptr() if jets is not None else None,
+                                                 st.ws.data_ptr(), st.ws.numel(), status.data_ptr(), stream)
+                _lib.check(rc)
+                st.token = next(_stash_tokens)
+                stash_out.append(st.token)
+                subs = []
+        for sub in subs:
             desc = make_desc(grid, q, lo, hi, widths, act, act_param, sub, precision)
             nbytes = lib.stpde_workspace_bytes(ctypes.byref(desc))
             if nbytes == 0:
@@ -194,8 +238,11 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
 def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
                  Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
                  spec: JetSpec, precision: str, gy: torch.Tensor, gjets: Optional[torch.Tensor],
-                 need_grid: bool = True, check: bool = True):
+                 need_grid: bool = True, check: bool = True, stash_token: int = 0):
     """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l]).
+
+    ``stash_token``: token of the training forward whose planes may still sit in the device's stash workspace; if it
+    is still current the forward is not recomputed.
 
     Replaces what ``loss.backward()`` does in the reference (experiments/rb2d/train.py:77) for the decode +
     PDE-derivative part of the graph: autograd's backward through every ``torch.autograd.grad`` call of
@@ -225,7 +272,9 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
         nbytes = lib.stpde_backward_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             raise _lib.StpdeError(-1, lib.stpde_last_error().decode())
-        ws = _workspace(device, nbytes)
+        st = _stashes.get(device)
+        reuse = 1 if (stash_token and st is not None and st.token == stash_token and st.ws.numel() >= nbytes) else 0
+        ws = st.ws if reuse else _workspace(device, nbytes)
         # The adjoints travel through fp16 hi/lo planes behind a power-of-two scale; if one overflows (status bit 1)
         # the sweep is repeated with 6 more bits of headroom.
         for headroom in (0, 6, 12, 24):
@@ -234,7 +283,7 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
             rc = lib.stpde_jet_backward(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr, bptr,
                                         gy.data_ptr(), gjets.data_ptr() if spec.n_jet else None, gwptr, gbptr,
                                         ggrid.data_ptr() if ggrid is not None else None, ws.data_ptr(), ws.numel(),
-                                        status.data_ptr(), stream)
+                                        reuse, status.data_ptr(), stream)
             _lib.check(rc)
             if not sync or not (int(status.item()) & 2):
                 break
@@ -263,7 +312,13 @@ class FusedJetQuery(torch.autograd.Function):
     def forward(ctx, grid, q, lo, hi, act, act_param_t, spec, precision, n_layers, *params):
         Ws, bs = params[:n_layers], params[n_layers:]
         beta = float(act_param_t.detach()) if act_param_t is not None else 1.0
-        y, jets = raw_forward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision)
+        needs = ctx.needs_input_grad
+        stash_out = None
+        if (needs[0] or any(needs[9:])) and fused_backward_supported(q, spec, n_layers, needs[1],
+                                                                    act_param_t is not None and needs[5]):
+            stash_out = []            # training forward: keep the operand planes for the backward when they fit
+        y, jets = raw_forward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, stash_out=stash_out)
+        ctx.stash_token = stash_out[0] if stash_out else 0
         ctx.save_for_backward(grid, q, act_param_t if act_param_t is not None else torch.empty(0), *params)
         ctx.meta = (lo, hi, act, spec, n_layers, act_param_t is not None)
         ctx.precision = precision
@@ -288,7 +343,7 @@ class FusedJetQuery(torch.autograd.Function):
             if spec.n_jet > 0 and gj is None:
                 gj = torch.zeros(spec.n_jet, *gy.shape, dtype=gy.dtype, device=gy.device)
             ggrid, gW, gB = raw_backward(grid, q, lo, hi, params[:n_layers], params[n_layers:], act, beta, spec,
-                                         ctx.precision, gy, gj, need_grid=needs[0])
+                                         ctx.precision, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
             if needs[0]:
                 result[0] = ggrid
             for i, g in enumerate(list(gW) + list(gB)):

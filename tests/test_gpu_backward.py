@@ -175,3 +175,58 @@ def test_backward_fallback_routes(dev):
     y = sp.query_local_implicit_grid(model, grid, q, 0., 1.)
     y.sum().backward()
     assert q.grad is not None and torch.isfinite(q.grad).all()
+
+
+def test_training_forward_stash_is_reused_and_invalidated(dev):
+    """stpde_jet_forward_train keeps the chunk's planes; the backward with the current token skips the recompute and
+    gives the same gradients as the recomputing backward; a later training forward invalidates the token."""
+    gen = torch.Generator().manual_seed(9)
+    d, c, o, nf, p = 3, 16, 4, 8, 1000
+    Ws, bs = make_decoder(gen, d, c, o, nf, dev)
+    grid = (torch.randn(1, 3, 4, 5, c, generator=gen) * 0.5).to(dev)
+    q = (torch.rand(1, p, d, generator=gen) * (1 - 2e-6) + 1e-6).to(dev)
+    spec = JetSpec(*RB2)
+    gy = torch.randn(1, p, o, generator=gen).to(dev)
+    gj = (torch.randn(spec.n_jet, 1, p, o, generator=gen) * 0.05).to(dev)
+    lo, hi = jets.bounds_tensors(0., 1., d, dev)
+    y0, j0 = jets.raw_forward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3")
+    tok = []
+    y1, j1 = jets.raw_forward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", stash_out=tok)
+    assert len(tok) == 1 and tok[0] > 0
+    assert rel_linf(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-6          # same arithmetic, pair kernel for every layer
+    assert rel_linf(j1.cpu().numpy(), j0.cpu().numpy()) < 2e-6
+    ref = jets.raw_backward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", gy, gj)
+    reuse = jets.raw_backward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", gy, gj, stash_token=tok[0])
+    again = jets.raw_backward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", gy, gj, stash_token=tok[0])
+    for a, b, c_ in zip([ref[0]] + ref[1] + ref[2], [reuse[0]] + reuse[1] + reuse[2], [again[0]] + again[1] + again[2]):
+        assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < 2e-6         # atomics reorder the sums, nothing else differs
+        assert rel_linf(c_.cpu().numpy(), a.cpu().numpy()) < 2e-6
+    # another training forward (different points) replaces the stash: the old token must not be honoured
+    q2 = (torch.rand(1, p, d, generator=gen) * (1 - 2e-6) + 1e-6).to(dev)
+    tok2 = []
+    jets.raw_forward(grid, q2, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", stash_out=tok2)
+    stale = jets.raw_backward(grid, q, lo, hi, Ws, bs, "tanh", 1.0, spec, "fp16x3", gy, gj, stash_token=tok[0])
+    assert rel_linf(stale[0].cpu().numpy(), ref[0].cpu().numpy()) < 2e-6
+    assert tok2[0] != tok[0]
+
+
+def test_chunked_training_accumulates_like_one_batch(dev):
+    """Walking the batch in chunks (each with its own stash) accumulates the same .grad as one big backward."""
+    torch.manual_seed(2)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = (torch.randn(1, 4, 6, 5, 16) * 0.5).to(dev).requires_grad_(True)
+    q = torch.rand(1, 3000, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+
+    def run(chunk):
+        model.zero_grad()
+        grid.grad = None
+        for s0 in range(0, q.shape[1], chunk):
+            y, res = layer(q[:, s0:s0 + chunk])
+            (y.abs().sum() + 0.0125 * torch.stack(list(res.values())).abs().sum()).backward()
+        return [grid.grad.clone()] + [p_.grad.clone() for p_ in model.parameters()]
+
+    whole, parts = run(3000), run(700)
+    for a, b in zip(parts, whole):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5

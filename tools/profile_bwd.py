@@ -20,11 +20,19 @@ grid, q = bench.synthetic_inputs(1234, dev, npts)
 grid.requires_grad_(True)
 layer = sp.get_rb2_pde_layer(**bench.RB2)
 layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
-for _ in range(steps):
+from space_time_pde_b200 import _lib
+lib = _lib.load()
+for it in range(steps):
+    if it == steps - 1 and os.environ.get("STPDE_PRINT_PROFILE"):
+        torch.cuda.synchronize()
+        lib.stpde_profile_enable(1)
+        _lib.profile_read()
     model.zero_grad()
     grid.grad = None
     y, res = layer(q)
     loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
     loss.backward()
 torch.cuda.synchronize()
+if os.environ.get("STPDE_PRINT_PROFILE"):
+    print({k: round(v[0], 2) for k, v in _lib.profile_read().items() if v[1] > 0})
 print("ok", float(loss), float(grid.grad.abs().max()))
