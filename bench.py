@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-chunk", type=int, default=16384, help="query points per forward/backward chunk of the training leg")
     ap.add_argument("--train-workspace-mb", type=int, default=40960, help="workspace budget of the training leg (stash of one chunk)")
+    ap.add_argument("--train-backward-precision", default="same", choices=["same", "fp16x3", "fp16"],
+                    help="arithmetic of the reverse sweep's contractions (same = the forward's parity mode)")
     ap.add_argument("--train-steps", type=int, default=1,
                     help="timed training steps (forward + residuals + loss + fused backward [+ all-reduce]); 0 skips the leg")
     args = ap.parse_args()
@@ -345,6 +347,7 @@ def main():
         # gradients accumulate in .grad across chunks exactly as one big backward would.
         os.environ["STPDE_WORKSPACE_MB"] = str(args.train_workspace_mb)
         jets.release_workspaces()
+        jets.set_backward_precision(args.train_backward_precision)
         tchunk = args.train_chunk
 
         def train_step():
@@ -381,6 +384,7 @@ def main():
         # of the forward inside the backward is overhead, not counted
         train = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
                  "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
+                 "backward_precision": args.precision if args.train_backward_precision == "same" else args.train_backward_precision,
                  "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients), "
                          "chunks of the batch with the forward planes kept for the backward (no recompute)"
                          + (" + one NCCL all-reduce of the flat gradient buffer" if world > 1 else ""),
@@ -392,6 +396,7 @@ def main():
         for p_ in params:
             p_.grad = None
         jets.release_workspaces()
+        jets.set_backward_precision("same")
         layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
 
     if world > 1:

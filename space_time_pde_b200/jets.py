@@ -30,6 +30,19 @@ def set_test_backend(fn) -> None:
     _test_backend = fn
 
 
+# Arithmetic of the reverse sweep's contractions: "same" follows the forward precision (fp32 / fp16x3 -> 3-pass
+# split, the parity mode); "fp16" runs dgrad / wgrad as single fp16 passes (mixed-precision training: gradients
+# accurate to ~1e-3, 3x fewer tensor-core MMAs).
+BACKWARD_PRECISION = os.environ.get("STPDE_BACKWARD_PRECISION", "same")
+
+
+def set_backward_precision(name: str) -> None:
+    global BACKWARD_PRECISION
+    if name not in ("same", "fp16", "fp16x3"):
+        raise ValueError("backward precision must be 'same', 'fp16x3' or 'fp16'")
+    BACKWARD_PRECISION = name
+
+
 def set_default_precision(name: str) -> None:
     global DEFAULT_PRECISION
     if name not in _lib.PRECISIONS:
@@ -97,6 +110,7 @@ class _Stash:
     def __init__(self, ws: torch.Tensor):
         self.ws = ws
         self.token = 0
+        self.precision = ""      # arithmetic of the forward that filled it (a single-pass forward leaves no lo planes)
 
 
 _stashes: Dict[torch.device, _Stash] = {}
@@ -203,6 +217,7 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
                                                  st.ws.data_ptr(), st.ws.numel(), status.data_ptr(), stream)
                 _lib.check(rc)
                 st.token = next(_stash_tokens)
+                st.precision = precision
                 stash_out.append(st.token)
                 subs = []
         for sub in subs:
@@ -273,7 +288,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
         if nbytes == 0:
             raise _lib.StpdeError(-1, lib.stpde_last_error().decode())
         st = _stashes.get(device)
-        reuse = 1 if (stash_token and st is not None and st.token == stash_token and st.ws.numel() >= nbytes) else 0
+        reuse = 1 if (stash_token and st is not None and st.token == stash_token and st.ws.numel() >= nbytes
+                      and (precision == "fp16" or st.precision != "fp16")) else 0
         ws = st.ws if reuse else _workspace(device, nbytes)
         # The adjoints travel through fp16 hi/lo planes behind a power-of-two scale; if one overflows (status bit 1)
         # the sweep is repeated with 6 more bits of headroom.
@@ -342,8 +358,9 @@ class FusedJetQuery(torch.autograd.Function):
             gj = gjets if (spec.n_jet > 0 and gjets is not None and gjets.numel() > 0) else None
             if spec.n_jet > 0 and gj is None:
                 gj = torch.zeros(spec.n_jet, *gy.shape, dtype=gy.dtype, device=gy.device)
+            bprec = ctx.precision if BACKWARD_PRECISION == "same" else BACKWARD_PRECISION
             ggrid, gW, gB = raw_backward(grid, q, lo, hi, params[:n_layers], params[n_layers:], act, beta, spec,
-                                         ctx.precision, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
+                                         bprec, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
             if needs[0]:
                 result[0] = ggrid
             for i, g in enumerate(list(gW) + list(gB)):

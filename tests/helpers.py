@@ -71,3 +71,25 @@ def rel_err_quantile(a, b, q=0.995):
     b = np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return float(np.quantile(np.abs(a - b) / (den if den > 0 else 1.0), q))
+
+
+GRAD_CASES = ["rb2_tanh", "rb2_softplus", "rb2_elu", "rb2_paper_softplus", "rb2_nonunit_tanh",
+              "generic_d1_softplus", "generic_d2_softplus", "generic_d4_softplus"]
+
+
+def load_grads(name):
+    """Gradients of the training-style loss from the REAL reference (tests/golden/make_golden_grads.py, float64)."""
+    z = np.load(os.path.join(GOLDEN, "grads_" + name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def pde_layer_for(sp, name, case):
+    """The PDELayer of a golden case built on the product's API (RB2 or the custom strings)."""
+    if name in RB2_CASES:
+        return sp.get_rb2_pde_layer(**RB2_CASES[name])
+    dim, o = int(case["dim"]), case["Ws"][5].shape[0]
+    in_vars, out_vars, eqs = custom_equations(name, dim, o)
+    layer = sp.PDELayer(in_vars=", ".join(in_vars), out_vars=", ".join(out_vars))
+    for eq_name, (string, subs) in eqs.items():
+        layer.add_equation(string, eq_name, subs_dict=subs)
+    return layer

@@ -14,7 +14,8 @@ import torch
 import space_time_pde_b200 as sp
 from space_time_pde_b200 import _torch_jets, jets
 from space_time_pde_b200.equations import JetSpec
-from tests.helpers import rel_linf
+from tests.helpers import GRAD_CASES, load_case, load_grads, pde_layer_for, rel_linf
+from tests.test_host_logic import bounds, build_model
 
 pytestmark = pytest.mark.gpu
 BWD_TOLS = {"fp32": 5e-5, "fp16x3": 5e-5, "fp16": 5e-2}
@@ -230,3 +231,57 @@ def test_chunked_training_accumulates_like_one_batch(dev):
     whole, parts = run(3000), run(700)
     for a, b in zip(parts, whole):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_loss_backward_matches_reference_golden_gradients(name, dev):
+    """PDELayer + training-style loss + loss.backward() on the GPU (fused forward, fused reverse sweep) against the
+    gradients of the REAL reference (float64, tests/golden/make_golden_grads.py).  Tolerance 1e-4 rel-L-infinity per
+    tensor: the golden losses are means, so the cotangents are ~1e-3 .. 1e-2 and exercise the adjoint rescaling."""
+    c, g = load_case(name), load_grads(name)
+    o = c["Ws"][5].shape[0]
+    model = build_model(c, o).to(dev)
+    grid = torch.tensor(c["grid"]).to(dev).requires_grad_(True)
+    q = torch.tensor(c["q"]).to(dev)
+    xmin, xmax = bounds(c)
+    layer = pde_layer_for(sp, name, c)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, xmin, xmax))
+    y, res = layer(q, return_residue=True)
+    loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    errs = {"grid": rel_linf(grid.grad.cpu().numpy(), g["g_grid"])}
+    for i in range(6):
+        errs[f"W{i}"] = rel_linf(model.fc[i].weight.grad.cpu().numpy(), g[f"g_W{i}"])
+        errs[f"b{i}"] = rel_linf(model.fc[i].bias.grad.cpu().numpy(), g[f"g_b{i}"])
+    print(name, " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) < 1e-4, errs
+
+
+def test_single_pass_backward_option(dev):
+    """STPDE_BACKWARD_PRECISION=fp16: mixed-precision style reverse sweep (one fp16 pass) on a parity-mode forward."""
+    errs = run_case(dev, 3, (3, 4, 5), 16, 4, 8, "softplus", *RB2, p=2048, precision="fp16", seed=3)
+    assert max(errs.values()) < BWD_TOLS["fp16"], errs
+    jets.set_backward_precision("fp16")
+    try:
+        torch.manual_seed(3)
+        model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+        grid = (torch.randn(1, 4, 6, 5, 16) * 0.5).to(dev).requires_grad_(True)
+        q = torch.rand(1, 1000, 3, device=dev)
+        layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+
+        def grads():
+            model.zero_grad()
+            grid.grad = None
+            y, res = layer(q)
+            (y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()).backward()
+            return [grid.grad.clone()] + [p_.grad.clone() for p_ in model.parameters()]
+
+        low = grads()
+        jets.set_backward_precision("same")
+        full = grads()
+    finally:
+        jets.set_backward_precision("same")
+    for a, b in zip(low, full):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 5e-2

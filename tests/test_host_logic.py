@@ -12,7 +12,7 @@ import torch
 
 import space_time_pde_b200 as sp
 from space_time_pde_b200 import _lib, _torch_jets, equations, jets
-from tests.helpers import RB2_CASES, custom_equations, load_case, rel_linf
+from tests.helpers import GRAD_CASES, RB2_CASES, custom_equations, load_case, load_grads, pde_layer_for, rel_linf
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -239,3 +239,25 @@ def test_training_gradients_match_autograd_port(cpu_backend):
     for i in range(6):
         assert rel_linf(model.fc[i].weight.grad.numpy(), port.layers[i].weight.grad.numpy()) < 1e-4, i
         assert rel_linf(model.fc[i].bias.grad.numpy(), port.layers[i].bias.grad.numpy()) < 1e-4, i
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_torch_jet_checker_gradients_match_reference_golden(name, cpu_backend):
+    """Pins the CHECKER of the GPU backward tests: loss.backward() through the jet route with the torch-op jet
+    evaluator (float32 on CPU) against the real reference's float64 gradients (tests/golden/grads_*.npz)."""
+    c, g = load_case(name), load_grads(name)
+    o = c["Ws"][5].shape[0]
+    model = build_model(c, o)
+    grid = torch.tensor(c["grid"], requires_grad=True)
+    q = torch.tensor(c["q"])
+    xmin, xmax = bounds(c)
+    layer = pde_layer_for(sp, name, c)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, xmin, xmax))
+    y, res = layer(q, return_residue=True)
+    loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert rel_linf(grid.grad.numpy(), g["g_grid"]) < 2e-4
+    for i in range(6):
+        assert rel_linf(model.fc[i].weight.grad.numpy(), g[f"g_W{i}"]) < 2e-4, i
+        assert rel_linf(model.fc[i].bias.grad.numpy(), g[f"g_b{i}"]) < 2e-4, i
