@@ -442,6 +442,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without release semantics: the epilogue only hands the TMEM accumulator back (its tcgen05.ld results are
+// already in registers after tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The releasing form makes the
+// warp drain every global store / red of the tile first (MEMBAR.ALL.GPU + ERRBAR: ~8 % of the epilogue's stall
+// samples and the tile's TMEM buffer stays blocked for the whole drain).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t leader_bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -708,7 +715,10 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         // current one is evaluated (the dependent vertex gather of MODE 3 would otherwise serialise every row).
         constexpr int H = (MODE == kModeBwd0 || KC <= 3) ? 4 : 2;  // rows per step (register budget: 96 per thread)
         constexpr int PC = (MODE == kModeBwd) ? KC : 1;            // prefetched values per row
-        constexpr bool kPrefetch = (MODE == kModeBwd0) || KC <= 8;
+        // MODE 3 prefetches the next step's z0 into registers (dependent vertex gather); MODE 2 relies on the L2
+        // prefetch of the next tile below - a register double buffer of K values per row spills inside the hot loop
+        // and the spill store then waits for the load it was meant to hide.
+        constexpr bool kPrefetch = (MODE == kModeBwd0);
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
         const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
@@ -788,8 +798,8 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             float amax = 0.f;
 #pragma unroll 1
             for (int rb = sub; rb < NRB; rb += kEpiPQ) {
-#pragma unroll
-                for (int h = 0; h < 8 / H; ++h) {
+#pragma unroll 1
+                for (int h = 0; h < 8 / H; ++h) {                  // rolled: the unrolled epilogue overflowed the i-cache
                     const int rbase = r0 + rb * 8 + h * H;
                     uint32_t v[KC][H];
 #pragma unroll
@@ -912,7 +922,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
         }
     } else if (MODE < kModeBwd && warp < 2 + kEpiW) {
         // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
@@ -1025,7 +1035,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
         }
     }
     tc_fence_before();
