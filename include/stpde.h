@@ -219,6 +219,18 @@ int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_featur
                     int32_t n_eq, float *residuals, void *stream);
 
 /*
+ * Reverse mode of stpde_residuals (what autograd does for the lambdified equation arithmetic of src/pde.py:139-142
+ * inside loss.backward()).  The caller differentiates the equations symbolically and passes ONE postfix program per
+ * output symbol - y_0..y_{o-1}, then every (jet plane, output) entry in plane-major order - evaluating
+ *     sum_e gres[e] * d residual_e / d symbol ,   extra opcode  9 PUSH_GRES e   (gres: [n_eq, b, p])
+ * Outputs: gy [b,p,o], gjets [n_jet,b,p,o] (all entries written).  Limits: 2048 words, 256 constants.
+ */
+int stpde_residuals_backward(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                             const float *q, const int64_t *q_strides, const float *y, const float *jets,
+                             const int32_t *prog, int32_t prog_words, const float *consts, int32_t n_consts,
+                             int32_t n_eq, const float *gres, float *gy, float *gjets, void *stream);
+
+/*
  * Instrumentation (bench.py): every kernel launch is counted per slot; with profiling enabled each
  * launch group is additionally bracketed by CUDA events on the launching stream.
  * stpde_profile_read synchronises the device, fills elapsed milliseconds and launch counts per

@@ -49,7 +49,7 @@ EXPORTS = ["stpde_version", "stpde_last_error", "stpde_desc_size", "stpde_device
            "stpde_interp_coefficients", "stpde_interp", "stpde_jet_forward", "stpde_jet_forward_host",
            "stpde_backward_workspace_bytes", "stpde_backward_chunk_points", "stpde_jet_backward",
            "stpde_jet_forward_train",
-           "stpde_residuals", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
+           "stpde_residuals", "stpde_residuals_backward", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
 
 
 class StpdeError(RuntimeError):
@@ -138,6 +138,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.stpde_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), i64p, c_int]
     lib.stpde_profile_slot_name.restype = ctypes.c_char_p
     lib.stpde_profile_slot_name.argtypes = [c_int]
+    lib.stpde_residuals_backward.restype = c_int
+    lib.stpde_residuals_backward.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, i32p, i32, f32p,
+                                             i32, i32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stpde_residuals.restype = c_int
     lib.stpde_residuals.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, i32p, i32, f32p,
                                     i32, i32, c_void_p, c_void_p]

@@ -665,4 +665,42 @@ int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_featur
     return STPDE_OK;
 }
 
+int stpde_residuals_backward(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                             const float* q, const int64_t* q_strides, const float* y, const float* jets,
+                             const int32_t* prog, int32_t prog_words, const float* consts, int32_t n_consts, int32_t n_eq,
+                             const float* gres, float* gy, float* gjets, void* stream) {
+    static thread_local ResidualProgramBig rp;
+    if (prog_words < 0 || prog_words > 2048 || (prog_words & 1)) return fail(STPDE_EUNSUPPORTED, "adjoint program too long (%d words)", prog_words);
+    if (n_consts < 0 || n_consts > 256) return fail(STPDE_EUNSUPPORTED, "too many constants (%d)", n_consts);
+    if (!gres || !gy || (n_jet > 0 && !gjets)) return fail(STPDE_EINVAL, "null pointer argument");
+    const int n_out = out_features * (1 + n_jet);
+    int sp = 0, out = 0;
+    for (int w = 0; w < prog_words; w += 2) {
+        int op = prog[w], arg = prog[w + 1];
+        switch (op) {
+            case 0: if (arg < 0 || arg >= n_consts) return fail(STPDE_EINVAL, "const index"); ++sp; break;
+            case 1: if (arg < 0 || arg >= dim) return fail(STPDE_EINVAL, "q index"); ++sp; break;
+            case 2: if (arg < 0 || arg >= out_features) return fail(STPDE_EINVAL, "y index"); ++sp; break;
+            case 3: if (arg < 0 || arg >= n_jet * out_features) return fail(STPDE_EINVAL, "jet index"); ++sp; break;
+            case 9: if (arg < 0 || arg >= n_eq) return fail(STPDE_EINVAL, "gres index"); ++sp; break;
+            case 4: case 5: if (sp < 2) return fail(STPDE_EINVAL, "stack underflow"); --sp; break;
+            case 6: case 7: if (sp < 1) return fail(STPDE_EINVAL, "stack underflow"); break;
+            case 8: if (sp != 1) return fail(STPDE_EINVAL, "adjoint program leaves %d values", sp); sp = 0; ++out; break;
+            default: return fail(STPDE_EINVAL, "opcode %d", op);
+        }
+        if (sp > 16) return fail(STPDE_EUNSUPPORTED, "expression too deep");
+    }
+    if (out != n_out || sp != 0) return fail(STPDE_EINVAL, "adjoint program has %d outputs, expected %d", out, n_out);
+    rp.n_words = prog_words;
+    memcpy(rp.words, prog, prog_words * sizeof(int32_t));
+    memcpy(rp.consts, consts, n_consts * sizeof(float));
+    {
+        ProfScope ps(kSlotResidual, (cudaStream_t)stream);
+        launch_residuals_backward(rp, npts, (int64_t)batch * npts, dim, out_features, n_jet, n_eq, q, q_strides, y, jets, gres,
+                                  gy, gjets, (cudaStream_t)stream);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STPDE_OK;
+}
+
 }  // extern "C"

@@ -53,6 +53,15 @@ void launch_layer_gemm(const JetSpec& spec, int dim, int act, float beta, int ro
 void launch_final_blend(const JetSpec& spec, int dim, int rows, int pc, int64_t total_pts, int64_t p0, int Kp, int O,
                         const float* actIn, const float* Wlast, const float* blast, const ChunkBuffers& cb, float* y,
                         float* jets, cudaStream_t st);
+// adjoint programs (one per output symbol: o values, then n_jet * o jet entries) can be longer
+struct ResidualProgramBig {
+    int n_words;
+    int words[2048];
+    float consts[256];
+};
+void launch_residuals_backward(const ResidualProgramBig& prog, int npts, int64_t total_pts, int dim, int O, int n_jet,
+                               int n_eq, const float* q, const int64_t* qs, const float* y, const float* jets,
+                               const float* gres, float* gy, float* gjets, cudaStream_t st);
 void launch_residuals(const ResidualProgram& prog, int npts, int64_t total_pts, int dim, int O, int n_jet,
                       const float* q, const int64_t* qs, const float* y, const float* jets, float* residuals,
                       cudaStream_t st);

@@ -600,6 +600,48 @@ __global__ void residual_kernel(ResidualProgram prog, int npts, int64_t total_pt
     }
 }
 
+// Reverse mode of the residual programs: the host differentiates the equations symbolically and sends ONE postfix
+// program per output symbol s (values y_0..y_{o-1}, then every jet entry), each evaluating
+//     sum_e gres[e] * d residual_e / d s        (opcode 9 = PUSH_GRES e)
+// so the kernel is the same interpreter with a different store: gy [b*p][O], gjets [n_jet][b*p][O].
+__global__ void residual_backward_kernel(ResidualProgramBig prog, int npts, int64_t total_pts, int dim, int O, int n_jet,
+                                         int n_eq, const float* __restrict__ q, int64_t qs0, int64_t qs1, int64_t qs2,
+                                         const float* __restrict__ y, const float* __restrict__ jets,
+                                         const float* __restrict__ gres, float* __restrict__ gy,
+                                         float* __restrict__ gjets) {
+    for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < total_pts;
+         gp += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(gp / npts), p = (int)(gp % npts);
+        float st[16];
+        int sp = 0, out = 0;
+        for (int w = 0; w < prog.n_words; w += 2) {
+            const int op = prog.words[w], arg = prog.words[w + 1];
+            switch (op) {
+                case 0: st[sp++] = prog.consts[arg]; break;
+                case 1: st[sp++] = q[b * qs0 + p * qs1 + arg * qs2]; break;
+                case 2: st[sp++] = y[gp * O + arg]; break;
+                case 3: st[sp++] = jets[((int64_t)(arg / O) * total_pts + gp) * O + (arg % O)]; break;
+                case 4: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+                case 5: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+                case 6: st[sp - 1] = -st[sp - 1]; break;
+                case 7: {
+                    float base = st[sp - 1], r = 1.f;
+                    int n = arg < 0 ? -arg : arg;
+                    for (int t = 0; t < n; ++t) r *= base;
+                    st[sp - 1] = arg < 0 ? 1.f / r : r;
+                    break;
+                }
+                case 9: st[sp++] = gres[(int64_t)arg * total_pts + gp]; break;
+                default:  // END of the program of output symbol `out`
+                    if (out < O) gy[gp * O + out] = st[0];
+                    else gjets[((int64_t)((out - O) / O) * total_pts + gp) * O + ((out - O) % O)] = st[0];
+                    sp = 0; ++out;
+                    break;
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // host-side launchers
 // ----------------------------------------------------------------------------------------------
@@ -713,6 +755,14 @@ void launch_final_blend(const JetSpec& spec, int dim, int rows, int pc, int64_t 
                         float* jets, cudaStream_t st) {
     STPDE_DISPATCH_KC(spec.kc, launch_final_t<KC>(spec, dim, rows, pc, total_pts, p0, Kp, O, actIn, Wlast, blast, cb, y,
                                                   jets, st));
+}
+
+void launch_residuals_backward(const ResidualProgramBig& prog, int npts, int64_t total_pts, int dim, int O, int n_jet,
+                               int n_eq, const float* q, const int64_t* qs, const float* y, const float* jets,
+                               const float* gres, float* gy, float* gjets, cudaStream_t st) {
+    if (total_pts == 0) return;
+    residual_backward_kernel<<<grid_for(total_pts, 256), 256, 0, st>>>(prog, npts, total_pts, dim, O, n_jet, n_eq, q, qs[0],
+                                                                        qs[1], qs[2], y, jets, gres, gy, gjets);
 }
 
 void launch_residuals(const ResidualProgram& prog, int npts, int64_t total_pts, int dim, int O, int n_jet,

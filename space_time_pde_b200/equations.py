@@ -20,7 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import sympy
 from sympy.core.function import AppliedUndef
 
-OP_CONST, OP_Q, OP_Y, OP_JET, OP_ADD, OP_MUL, OP_NEG, OP_POWI, OP_END = range(9)
+OP_CONST, OP_Q, OP_Y, OP_JET, OP_ADD, OP_MUL, OP_NEG, OP_POWI, OP_END, OP_GRES = range(10)
 
 
 class UnsupportedEquation(NotImplementedError):
@@ -142,10 +142,10 @@ def _torch_namespace():
              "tanh": torch.tanh, "Abs": torch.abs}, "math"]
 
 
-def _postfix(e: sympy.Expr, in_vars, out_vars, jet_symbols):
+def _postfix(e: sympy.Expr, in_vars, out_vars, jet_symbols, g_symbols=(), consts=None):
     """Postfix words with symbolic jet operands: (OP_JET, (output, multi)) resolved at bind time."""
     words: List = []
-    consts: List[float] = []
+    consts = [] if consts is None else consts
 
     def const(v: float):
         v = float(v)
@@ -161,6 +161,8 @@ def _postfix(e: sympy.Expr, in_vars, out_vars, jet_symbols):
                 words.extend((OP_Q, in_vars.index(node)))
             elif node in out_vars:
                 words.extend((OP_Y, out_vars.index(node)))
+            elif node in g_symbols:
+                words.extend((OP_GRES, list(g_symbols).index(node)))
             else:
                 raise UnsupportedEquation(f"free symbol {node}")
         elif node.is_Number:
@@ -184,7 +186,7 @@ def _postfix(e: sympy.Expr, in_vars, out_vars, jet_symbols):
 
     emit(e)
     words.extend((OP_END, 0))
-    if len(consts) > 128:
+    if len(consts) > (256 if g_symbols else 128):
         raise UnsupportedEquation("too many constants")
     return words, consts
 
@@ -209,5 +211,49 @@ def bind_programs(equations: Sequence[CompiledEquation], spec: JetSpec, n_out: i
                 arg = spec.plane(multi) * n_out + oi
             words.extend((op, arg))
     if len(words) > 640 or len(consts) > 128:
+        return None
+    return words, consts
+
+
+def bind_adjoint_program(equations: Sequence[CompiledEquation], spec: JetSpec, in_vars, out_vars):
+    """Postfix programs of the REVERSE sweep through the residual arithmetic (``stpde_residuals_backward``).
+
+    One program per output symbol s - y_0..y_{o-1}, then every (jet plane, output) entry in plane-major order -
+    evaluating  sum_e G_e * d residual_e / d s  with G_e = d loss / d residual_e (opcode OP_GRES).  The equations are
+    differentiated symbolically; polynomial residuals stay polynomial.  None if a program cannot be built."""
+    in_vars, out_vars = list(in_vars), list(out_vars)
+    n_out = len(out_vars)
+    if any(ce is None or ce.program is None for ce in equations):
+        return None
+    g_syms = [sympy.Symbol(f"__gres{e}") for e in range(len(equations))]
+    jet_symbols: Dict[sympy.Symbol, Tuple[int, Tuple[int, ...]]] = {}
+    for ce in equations:
+        jet_symbols.update(ce.jet_symbols)
+    by_target = {v: k for k, v in jet_symbols.items()}
+    multis = [(k,) for k in spec.first] + [tuple(pair) for pair in spec.second]
+    targets: List[Optional[sympy.Symbol]] = list(out_vars)
+    for multi in multis:
+        for oi in range(n_out):
+            targets.append(by_target.get((oi, multi)))
+    words: List[int] = []
+    consts: List[float] = []
+    try:
+        for sym in targets:
+            total = sympy.Integer(0)
+            if sym is not None:
+                for ge, ce in zip(g_syms, equations):
+                    if ce.expr.has(sym):
+                        total = total + ge * sympy.diff(ce.expr, sym)
+            w, _ = _postfix(sympy.expand(total) if total != 0 else total, in_vars, out_vars, jet_symbols, g_syms, consts)
+            it = iter(w)
+            for op in it:
+                arg = next(it)
+                if op == OP_JET:
+                    oi, multi = arg
+                    arg = spec.plane(multi) * n_out + oi
+                words.extend((op, arg))
+    except UnsupportedEquation:
+        return None
+    if len(words) > 2048 or len(consts) > 256:
         return None
     return words, consts

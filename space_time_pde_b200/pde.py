@@ -9,6 +9,7 @@ elementwise kernel - no ``torch.autograd.grad`` sweeps.  For any other forward m
 behaves exactly like the reference (one autograd call per ``dif``).
 """
 import ctypes
+import os
 
 import sympy
 import torch
@@ -16,13 +17,58 @@ from sympy.parsing.sympy_parser import parse_expr
 from torch.autograd import grad
 
 from . import _lib
-from .equations import JetSpec, UnsupportedEquation, bind_programs, compile_equation
+from .equations import JetSpec, UnsupportedEquation, bind_adjoint_program, bind_programs, compile_equation
 from .jets import JetRequest, _i64
 
 
 def torch_diff(y, x):
     """d(sum y)/dx with a graph, as the reference's ``dif`` (src/pde.py:8-9)."""
     return grad(y, x, grad_outputs=torch.ones_like(y), create_graph=True, allow_unused=True)[0]
+
+
+class ResidualProgramFunction(torch.autograd.Function):
+    """Residuals of all equations from (y, jets) by the postfix-program kernel (``stpde_residuals``, replaces the
+    lambdified arithmetic of reference src/pde.py:139-142); backward = ``stpde_residuals_backward`` with the
+    symbolically differentiated programs (what autograd does for that arithmetic inside ``loss.backward()``)."""
+
+    @staticmethod
+    def forward(ctx, y, jets, xq, n_in, n_out, n_jet, n_eq, program, adjoint):
+        words, consts = program
+        b, p = xq.shape[0], xq.shape[1]
+        yc = y.detach().contiguous()
+        jc = jets.detach().contiguous() if n_jet else yc
+        res = torch.empty(n_eq, b, p, dtype=torch.float32, device=y.device)
+        lib = _lib.load()
+        with torch.cuda.device(y.device):
+            rc = lib.stpde_residuals(b, p, n_in, n_out, n_jet, xq.data_ptr(), _i64(xq.stride()), yc.data_ptr(),
+                                     jc.data_ptr(), (ctypes.c_int32 * len(words))(*words), len(words),
+                                     (ctypes.c_float * max(1, len(consts)))(*consts), len(consts), n_eq,
+                                     res.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(yc, jc, xq)
+        ctx.meta = (n_in, n_out, n_jet, n_eq, adjoint)
+        return res
+
+    @staticmethod
+    def backward(ctx, gres):
+        yc, jc, xq = ctx.saved_tensors
+        n_in, n_out, n_jet, n_eq, adjoint = ctx.meta
+        if adjoint is None:
+            raise RuntimeError("residual programs have no adjoint program (internal error: route selection)")
+        words, consts = adjoint
+        b, p = xq.shape[0], xq.shape[1]
+        g = gres.detach().to(torch.float32).contiguous()
+        gy = torch.empty(b, p, n_out, dtype=torch.float32, device=g.device)
+        gj = torch.empty(n_jet, b, p, n_out, dtype=torch.float32, device=g.device) if n_jet else None
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            rc = lib.stpde_residuals_backward(b, p, n_in, n_out, n_jet, xq.data_ptr(), _i64(xq.stride()), yc.data_ptr(),
+                                              jc.data_ptr(), (ctypes.c_int32 * len(words))(*words), len(words),
+                                              (ctypes.c_float * max(1, len(consts)))(*consts), len(consts), n_eq,
+                                              g.data_ptr(), gy.data_ptr(), gj.data_ptr() if gj is not None else None,
+                                              torch.cuda.current_stream(g.device).cuda_stream)
+        _lib.check(rc)
+        return gy, gj, None, None, None, None, None, None, None
 
 
 class PDELayer(object):
@@ -43,6 +89,7 @@ class PDELayer(object):
         self.eqns_jet = {}   # CompiledEquation or None (fused forward method)
         self.forward_method = None
         self._bound = None   # cache: (JetSpec, program) for the current equation set
+        self._adjoint = None # cache: adjoint programs (reverse sweep through the residual arithmetic)
 
     def add_equation(self, eqn_str, eqn_name='', subs_dict=None):
         """Register the residue expression ``eqn_str`` (see reference src/pde.py:36-86)."""
@@ -97,27 +144,21 @@ class PDELayer(object):
             spec = self.jet_spec()
             program = bind_programs(list(self.eqns_jet.values()), spec, self.n_out) if spec is not None else None
             self._bound = (spec, program)
+            self._adjoint = None
+            if program is not None:
+                self._adjoint = bind_adjoint_program(list(self.eqns_jet.values()), spec, self.in_vars, self.out_vars)
         return self._bound
 
     def _residues_from_jets(self, x_, y, jets):
         spec, program = self._binding()
         names = list(self.eqns_raw.keys())
         differentiable = torch.is_grad_enabled() and (y.requires_grad or (jets is not None and jets.requires_grad))
-        if program is not None and y.is_cuda and not differentiable and x_.dim() == 3 and names:
-            words, consts = program
-            b, p = x_.shape[0], x_.shape[1]
-            xq = x_.detach()
-            res = torch.empty(len(names), b, p, dtype=torch.float32, device=y.device)
-            jets_c = jets.contiguous() if jets is not None else y
-            yc = y.detach().contiguous()
-            lib = _lib.load()
-            with torch.cuda.device(y.device):
-                rc = lib.stpde_residuals(b, p, self.n_in, self.n_out, spec.n_jet, xq.data_ptr(), _i64(xq.stride()),
-                                         yc.data_ptr(), jets_c.data_ptr(),
-                                         (ctypes.c_int32 * len(words))(*words), len(words),
-                                         (ctypes.c_float * max(1, len(consts)))(*consts), len(consts), len(names),
-                                         res.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
-            _lib.check(rc)
+        kernel_ok = (program is not None and y.is_cuda and x_.dim() == 3 and names and y.dtype == torch.float32
+                     and os.environ.get("STPDE_RESIDUALS", "kernel") != "torch")
+        if kernel_ok and (not differentiable or self._adjoint is not None):
+            jets_in = jets if jets is not None else y.new_empty(0)
+            res = ResidualProgramFunction.apply(y, jets_in, x_.detach(), self.n_in, self.n_out, spec.n_jet, len(names),
+                                                program, self._adjoint)
             return {name: res[i].unsqueeze(-1) for i, name in enumerate(names)}
         # differentiable route: plain elementwise torch arithmetic on the jet tensors
         residues = {}

@@ -285,3 +285,28 @@ def test_single_pass_backward_option(dev):
         jets.set_backward_precision("same")
     for a, b in zip(low, full):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 5e-2
+
+
+def test_residual_program_backward_matches_torch_route(dev, monkeypatch):
+    """loss.backward() with the residual arithmetic in CUDA (stpde_residuals + stpde_residuals_backward) against the
+    same step with the lambdified torch arithmetic (STPDE_RESIDUALS=torch)."""
+    torch.manual_seed(5)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid0 = (torch.randn(2, 4, 6, 5, 16) * 0.5).to(dev)
+    q = torch.rand(2, 700, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(mean=[0.1, -0.2, 0.05, 0.3], std=[1.1, 0.9, 1.3, 0.7], t_crop=2., z_crop=1., x_crop=2.,
+                                 use_continuity=True)
+
+    def grads(route):
+        monkeypatch.setenv("STPDE_RESIDUALS", route)
+        grid = grid0.clone().requires_grad_(True)
+        model.zero_grad()
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        y, res = layer(q, return_residue=True)
+        loss = (y ** 2).mean() + 0.0125 * (torch.stack(list(res.values())) ** 2).mean()
+        loss.backward()
+        return [loss.detach(), grid.grad.clone()] + [p_.grad.clone() for p_ in model.parameters()]
+
+    kern, ref = grads("kernel"), grads("torch")
+    for i, (a, b) in enumerate(zip(kern, ref)):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5, i

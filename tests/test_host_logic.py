@@ -261,3 +261,73 @@ def test_torch_jet_checker_gradients_match_reference_golden(name, cpu_backend):
     for i in range(6):
         assert rel_linf(model.fc[i].weight.grad.numpy(), g[f"g_W{i}"]) < 2e-4, i
         assert rel_linf(model.fc[i].bias.grad.numpy(), g[f"g_b{i}"]) < 2e-4, i
+
+
+def _run_postfix(words, consts, q, y, jets, gres=None):
+    """Reference interpreter of the residual / adjoint programs (mirrors residual_kernel, numpy float64)."""
+    outs, st = [], []
+    it = iter(words)
+    for op in it:
+        arg = next(it)
+        if op == 0: st.append(np.full(y.shape[:-1], consts[arg]))
+        elif op == 1: st.append(q[..., arg])
+        elif op == 2: st.append(y[..., arg])
+        elif op == 3: st.append(jets[arg // y.shape[-1]][..., arg % y.shape[-1]])
+        elif op == 4: b = st.pop(); st[-1] = st[-1] + b
+        elif op == 5: b = st.pop(); st[-1] = st[-1] * b
+        elif op == 6: st[-1] = -st[-1]
+        elif op == 7: st[-1] = st[-1] ** arg
+        elif op == 9: st.append(gres[arg])
+        else:
+            outs.append(st.pop())
+            assert not st
+    return outs
+
+
+@pytest.mark.parametrize("kind", ["rb2", "rb2_normalised", "ns3d", "generic_d2"])
+def test_adjoint_programs_match_autograd_of_the_equations(kind):
+    """The symbolically differentiated adjoint programs (stpde_residuals_backward) against torch.autograd through the
+    lambdified equations, on random (q, y, jets, gres)."""
+    if kind == "rb2":
+        layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    elif kind == "rb2_normalised":
+        layer = sp.get_rb2_pde_layer(**RB2_CASES["rb2_paper_softplus"])
+    else:
+        name = "ns3d_swish" if kind == "ns3d" else "generic_d2_softplus"
+        in_vars, out_vars, eqs = custom_equations(name, 2, 3)
+        layer = sp.PDELayer(in_vars=", ".join(in_vars), out_vars=", ".join(out_vars))
+        for eq_name, (string, subs) in eqs.items():
+            layer.add_equation(string, eq_name, subs_dict=subs)
+    spec, program = layer._binding()
+    assert program is not None and layer._adjoint is not None
+    rng = np.random.default_rng(0)
+    b, p, d, o = 2, 17, layer.n_in, layer.n_out
+    q = rng.normal(size=(b, p, d)); y = rng.normal(size=(b, p, o)); jets_ = rng.normal(size=(spec.n_jet, b, p, o))
+    names = list(layer.eqns_raw.keys())
+    gres = rng.normal(size=(len(names), b, p))
+    res = _run_postfix(*program, q, y, jets_)
+    qt = torch.tensor(q); yt = torch.tensor(y, requires_grad=True); jt = torch.tensor(jets_, requires_grad=True)
+    total = 0.
+    for e, name in enumerate(names):
+        ce = layer.eqns_jet[name]
+        args = []
+        for s_ in ce.arg_symbols:
+            if s_ in ce.jet_symbols:
+                oi, multi = ce.jet_symbols[s_]
+                args.append(jt[spec.plane(multi)][..., oi])
+            elif s_ in layer.in_vars:
+                args.append(qt[..., layer.in_vars.index(s_)])
+            else:
+                args.append(yt[..., layer.out_vars.index(s_)])
+        val = ce.torch_fn(*args)
+        assert np.allclose(res[e], val.detach().numpy(), rtol=1e-9, atol=1e-9)
+        total = total + (val * torch.tensor(gres[e])).sum()
+    gy, gj = torch.autograd.grad(total, [yt, jt], allow_unused=True)
+    adj = _run_postfix(*layer._adjoint, q, y, jets_, gres)
+    assert len(adj) == o * (1 + spec.n_jet)
+    for i in range(o):
+        assert np.allclose(adj[i], gy[..., i].numpy(), rtol=1e-9, atol=1e-9)
+    for pl in range(spec.n_jet):
+        for i in range(o):
+            ref = gj[pl][..., i].numpy() if gj is not None else 0.
+            assert np.allclose(adj[o + pl * o + i], ref, rtol=1e-9, atol=1e-9)
