@@ -151,6 +151,76 @@ def gpu_eager_rate(device, batch=2048, batches=3):
             "sample": f"{batches} pseudo-batches of {batch} points, torch eager fp32 on the same GPU (oracle/ref_port.py)"}
 
 
+def reference_size_train_step(device, with_eager):
+    """Training step of the reference's own size (experiments/rb2d/train.py defaults: 10 crops x 1024 query points,
+    ImNet nf=32, latent 4x16x16x32, RB2 + continuity, L1 losses): ms per step of the fused path, of the same forward
+    with the autograd re-evaluation backward, and (context, like torch_eager_gpu) of the reference algorithm as
+    PyTorch eager ops on this GPU (oracle/ref_port.py).  The UNet3d encoder is out of scope: the latent grid is a leaf."""
+    import space_time_pde_b200 as sp
+    B, P, nf = 10, 1024, 32
+    torch.manual_seed(0)
+    model = sp.ImNet(dim=3, in_features=CHANNELS, out_features=4, nf=nf, activation=sp.NONLINEARITIES[ACT]).to(device)
+    grid = (torch.randn(B, *GRID, CHANNELS) * 0.5).to(device).requires_grad_(True)
+    q = torch.rand(B, P, 3, device=device)
+    target = torch.randn(B, P, 4, device=device)
+    layer = sp.get_rb2_pde_layer(**RB2)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+
+    def fused_step():
+        model.zero_grad(set_to_none=True)
+        grid.grad = None
+        y, res = layer(q, return_residue=True)
+        loss = torch.nn.functional.l1_loss(y, target) + 0.0125 * torch.stack(list(res.values())).abs().mean()
+        loss.backward()
+        return loss
+
+    def time_it(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {"config": f"{B} crops x {P} points, ImNet nf={nf} {ACT}, latent 4x16x16x32, RB2 + continuity, L1 losses"}
+    out["fused_ms"] = time_it(fused_step, 20)
+    out["points_per_s"] = B * P / (out["fused_ms"] * 1e-3)
+    os.environ["STPDE_BACKWARD"] = "torch"
+    os.environ["STPDE_RESIDUALS"] = "torch"
+    try:
+        out["torch_autograd_backward_ms"] = time_it(fused_step, 5)
+    finally:
+        os.environ.pop("STPDE_BACKWARD", None)
+        os.environ.pop("STPDE_RESIDUALS", None)
+    if with_eager:
+        from oracle import jet_oracle as jo
+        from oracle import ref_port as rp
+        port = rp.SkipMLP([l.weight.detach().cpu().numpy() for l in model.fc],
+                          [l.bias.detach().cpu().numpy() for l in model.fc], ACT).to(device)
+        iv, ov, eqs = jo.rb2_equations(**RB2)
+        exprs = rp.compile_equations(eqs)
+        grid2 = grid.detach().clone().requires_grad_(True)
+
+        def eager_step():
+            port.zero_grad(set_to_none=True)
+            grid2.grad = None
+            y, res = rp.values_and_residuals(port, grid2, q, 0., 1., iv, ov, exprs)
+            loss = torch.nn.functional.l1_loss(y, target) + 0.0125 * torch.stack(list(res.values())).abs().mean()
+            loss.backward()
+            return loss
+
+        try:
+            out["reference_algorithm_eager_gpu_ms"] = time_it(eager_step, 3)
+        except Exception as exc:
+            out["reference_algorithm_eager_gpu_ms"] = None
+            out["eager_error"] = str(exc)[:100]
+    return out
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -413,6 +483,11 @@ def main():
                 eager = gpu_eager_rate(device)
             except Exception as exc:   # e.g. out of memory for the autograd tapes
                 eager = {"error": str(exc)[:120]}
+        if train is not None and world == 1:
+            try:
+                train["reference_size_step"] = reference_size_train_step(device, with_eager=not args.no_cpu_baseline)
+            except Exception as exc:
+                train["reference_size_step"] = {"error": str(exc)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

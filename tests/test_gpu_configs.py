@@ -1,0 +1,120 @@
+"""GPU tests (-m gpu): the other BASELINE.json configurations as parity cases.
+
+  config 3  paper-like training shape: 8 crops, ImNet nf=32, normalised RB2 equations, single-pass fp16 MLP (relaxed parity)
+  config 4  custom PDELayer strings: 4-d incompressible Navier-Stokes with Laplacians, ImNet nf=256, K = 8 jet components
+  config 5  throughput-sweep shape: latent 32x32x32x128, ImNet nf=32, RB2
+Each is checked on a slice of its points against the fp64 numpy oracle (values, every requested partial), and config 5
+also runs the fused reverse sweep against float64 autograd of the torch jets (32768 vertices x 128 channels exercise
+the vertex-adjoint kernels' tiling)."""
+import numpy as np
+import pytest
+import torch
+
+import space_time_pde_b200 as sp
+from oracle import jet_oracle as jo
+from space_time_pde_b200 import jets
+from space_time_pde_b200.equations import JetSpec
+from tests.helpers import rel_linf
+from tests.test_gpu_backward import reference_grads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need CUDA (the hot path has no CPU fallback)"
+    return torch.device("cuda:0")
+
+
+def oracle_check(model, grid, q, act, spec, y, jt, n_check, tol):
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    yj = jo.query_jet(grid.cpu().numpy(), q[:, :n_check].cpu().numpy(), 0., 1., Ws, bs, act)
+    errs = {"y": rel_linf(y[:, :n_check].cpu().numpy(), yj.v)}
+    planes = [yj.g[a] for a in spec.first] + [yj.h[a][b] for a, b in spec.second]
+    for i, ref in enumerate(planes):
+        errs[f"jet{i}"] = rel_linf(jt[i][:, :n_check].cpu().numpy(), ref)
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < tol, errs
+
+
+def test_config3_paper_training_shape_fp16(dev):
+    torch.manual_seed(3)
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=32, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(8, 4, 16, 16, 32, device=dev) * 0.5
+    q = torch.rand(8, 8192, 3, device=dev) * (1 - 2e-6) + 1e-6
+    layer = sp.get_rb2_pde_layer(mean=[0.1, -0.2, 0.05, 0.3], std=[1.1, 0.9, 1.3, 0.7], t_crop=2., z_crop=1., x_crop=2.,
+                                 prandtl=1., rayleigh=1e6, use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    out = {}
+    for prec in ("fp16", "fp16x3"):
+        jets.set_default_precision(prec)
+        try:
+            with torch.no_grad():
+                y, res = layer(q)
+        finally:
+            jets.set_default_precision("fp16x3")
+        out[prec] = (y, res)
+    # relaxed mode against the parity mode (itself pinned to the oracle / golden vectors elsewhere): 3e-2
+    assert rel_linf(out["fp16"][0].cpu().numpy(), out["fp16x3"][0].cpu().numpy()) < 3e-3
+    for k in out["fp16"][1]:
+        assert rel_linf(out["fp16"][1][k].cpu().numpy(), out["fp16x3"][1][k].cpu().numpy()) < 3e-2, k
+    # parity mode against the oracle on a slice of crop 0
+    spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid[:1], q[:1], 0., 1., list(model.fc), "softplus", None, spec=spec)
+    oracle_check(model, grid[:1], q[:1], "softplus", spec, y, jt, 256, 1e-5)
+
+
+def test_config4_ns4d_width256_second_order(dev):
+    torch.manual_seed(4)
+    model = sp.ImNet(dim=4, in_features=32, out_features=4, nf=256, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 8, 8, 8, 8, 32, device=dev) * 0.5
+    q = torch.rand(1, 4096, 4, device=dev) * (1 - 2e-6) + 1e-6
+    layer = sp.PDELayer(in_vars="x, y, z, t", out_vars="u, v, w, p")
+    lap = lambda f: f"(dif(dif({f},x),x)+dif(dif({f},y),y)+dif(dif({f},z),z))"
+    adv = lambda f: f"(u*dif({f},x)+v*dif({f},y)+w*dif({f},z))"
+    for f in "uvw":
+        layer.add_equation(f"dif({f},t)+{adv(f)}+dif(p,{'xyz'['uvw'.index(f)]})-0.01*{lap(f)}", "mom_" + f)
+    layer.add_equation("dif(u,x)+dif(v,y)+dif(w,z)", "continuity")
+    spec = layer.jet_spec()
+    assert 1 + len(spec.first) + len(spec.second) == 8        # value + 4 first + 3 second (BASELINE config 4)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    with torch.no_grad():
+        yl, res = layer(q)
+        y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), "softplus", None, spec=spec)
+    assert torch.equal(yl, y) and all(torch.isfinite(v).all() for v in res.values())
+    # d = 4 blends 16 corners with 1/cubesize^2-scaled cancellations: 3e-5 on second derivatives (see test_gpu_parity)
+    oracle_check(model, grid, q, "softplus", spec, y, jt, 48, 3e-5)
+    # residuals from the same jets, evaluated by numpy from the oracle's planes
+    yj = jo.query_jet(grid.cpu().numpy(), q[:, :48].cpu().numpy(), 0., 1., [l.weight.detach().cpu().numpy() for l in model.fc],
+                      [l.bias.detach().cpu().numpy() for l in model.fc], "softplus")
+    cont = yj.g[0][..., 0] + yj.g[1][..., 1] + yj.g[2][..., 2]
+    assert rel_linf(res["continuity"][:, :48, 0].cpu().numpy(), cont) < 3e-5
+
+
+def test_config5_sweep_shape_forward_and_backward(dev):
+    torch.manual_seed(5)
+    model = sp.ImNet(dim=3, in_features=128, out_features=4, nf=32, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 32, 32, 32, 128, device=dev) * 0.3
+    q = torch.rand(1, 65536, 3, device=dev) * (1 - 2e-6) + 1e-6
+    spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
+    with torch.no_grad():
+        y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), "softplus", None, spec=spec)
+    # cubesize = 1/31: second derivatives carry 31^2 ~ 1e3 x the rounding of the value path
+    oracle_check(model, grid, q, "softplus", spec, y, jt, 256, 2e-5)
+    # reverse sweep on a subset (the float64 autograd checker keeps a tape of rows x widths)
+    n = 512
+    gen = torch.Generator().manual_seed(55)
+    gy = torch.randn(1, n, 4, generator=gen).to(dev)
+    gj = (torch.randn(spec.n_jet, 1, n, 4, generator=gen) * 1e-3).to(dev)
+    lo, hi = jets.bounds_tensors(0., 1., 3, dev)
+    Ws, bs = [l.weight.detach() for l in model.fc], [l.bias.detach() for l in model.fc]
+    ggrid, gW, gB = jets.raw_backward(grid, q[:, :n], lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3", gy, gj)
+    rgrid, rW, rB = reference_grads(grid, q[:, :n], lo, hi, Ws, bs, "softplus", 1.0, spec, gy, gj)
+    errs = {"grid": rel_linf(ggrid.cpu().numpy(), rgrid.cpu().numpy())}
+    for l in range(6):
+        errs[f"W{l}"] = rel_linf(gW[l].cpu().numpy(), rW[l].cpu().numpy())
+        errs[f"b{l}"] = rel_linf(gB[l].cpu().numpy(), rB[l].cpu().numpy())
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 5e-5, errs
