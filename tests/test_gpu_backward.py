@@ -310,3 +310,29 @@ def test_residual_program_backward_matches_torch_route(dev, monkeypatch):
     kern, ref = grads("kernel"), grads("torch")
     for i, (a, b) in enumerate(zip(kern, ref)):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5, i
+
+
+def test_encoder_gradients_through_permuted_latent_grid(dev, monkeypatch):
+    """The reference feeds the decoder a PERMUTED (non-contiguous) view of the UNet3d output (train.py:58-60).  A small
+    conv encoder stands in for it: its weight gradients through the fused path must match the torch route."""
+    torch.manual_seed(11)
+    enc = torch.nn.Conv3d(4, 16, 3, padding=1).to(dev)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    lres = torch.randn(2, 4, 4, 6, 5, device=dev)
+    q = torch.rand(2, 900, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+
+    def grads(route):
+        monkeypatch.setenv("STPDE_BACKWARD", route)
+        enc.zero_grad()
+        model.zero_grad()
+        latent = enc(lres).permute(0, 2, 3, 4, 1)                  # [b, T, Z, X, C], non-contiguous
+        assert not latent.is_contiguous()
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, latent, pts, 0., 1.))
+        y, res = layer(q, return_residue=True)
+        (y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()).backward()
+        return [enc.weight.grad.clone(), enc.bias.grad.clone(), model.fc[0].weight.grad.clone()]
+
+    fused, ref = grads("fused"), grads("torch")
+    for a, b in zip(fused, ref):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
