@@ -310,6 +310,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
         const int sub = (warp - 2) >> 2;
         const float scale = __ldg(args.wscale);
         const float act_scale = (float)(1 << kActScaleLog2);
+        const int n_first = spec.n_first;
         // skip connection + per-vertex latent/bias term of one 8-row block (independent loads, issued early)
         auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
 #pragma unroll
@@ -368,15 +369,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     s2 *= fmask;
 #pragma unroll
                     for (int c = 1; c < KC; ++c) {
-                        float za = 0.f, zb = 0.f;        // parents of a second-order component (0 for first order)
+                        o[c] = s1 * zt[c];
+                        if (c > n_first) {               // second order (warp-uniform): parents za, zb
+                            float za = 0.f, zb = 0.f;
 #pragma unroll
-                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                            if (1 + k < KC) {
-                                za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                if (1 + k < KC) {
+                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                }
                             }
+                            o[c] = fmaf(s2 * za, zb, o[c]);
                         }
-                        o[c] = fmaf(s2 * za, zb, s1 * zt[c]);    // first order: za = zb = 0
                     }
                     if (g_store && r < args.rows) {
                         const int64_t off = (int64_t)r * args.ld_out + g;
@@ -930,6 +934,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         const int sub = (warp - 2) >> 2;
         const float scale = __ldg(args.wscale);
         const float act_scale = (float)(1 << kActScaleLog2);
+        const int n_first = spec.n_first;
         auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -998,15 +1003,18 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                     s2 *= fmask;
 #pragma unroll
                     for (int c = 1; c < KC; ++c) {
-                        float za = 0.f, zb = 0.f;        // parents of a second-order component (0 for first order)
+                        o[c] = s1 * zt[c];
+                        if (c > n_first) {               // second order (warp-uniform): parents za, zb
+                            float za = 0.f, zb = 0.f;
 #pragma unroll
-                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                            if (1 + k < KC) {
-                                za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                if (1 + k < KC) {
+                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                }
                             }
+                            o[c] = fmaf(s2 * za, zb, o[c]);
                         }
-                        o[c] = fmaf(s2 * za, zb, s1 * zt[c]);
                     }
                     if (g_store && r < args.rows) {
                         const int64_t off = (int64_t)r * args.ld_out + g;
