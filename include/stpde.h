@@ -162,10 +162,12 @@ int stpde_jet_forward(const stpde_desc_t *desc, const float *grid, const int64_t
  *   gW[l] : [widths[l], in_l]  gradient of layer l's weight      (host array of n_layers device pointers)
  *   gB[l] : [widths[l]]        gradient of layer l's bias
  *   ggrid : [b, n_1..n_d, c]   gradient of the latent grid, CONTIGUOUS (may be NULL)
+ *   gbeta : [1]                gradient of act_param (the learnable beta of STPDE_ACT_SWISH, reference
+ *                              src/nonlinearities.py:5-13); may be NULL, untouched for other activations
  * All outputs are overwritten.  The forward is recomputed per chunk of points (no activations are kept between
  * the forward and the backward call); the contractions run on the tensor cores with the fp16 hi/lo split
  * (STPDE_PREC_FP32 and STPDE_PREC_FP16X3: 3 passes, STPDE_PREC_FP16: 1 pass).  Needs n_layers >= 3.
- * Gradients w.r.t. the query points and w.r.t. act_param are not produced.
+ * Gradients w.r.t. the query points are not produced.
  * status bit 1 reports an adjoint that left the fp16 range.  The adjoints are rescaled by a power of two S derived
  * from max|gy|, max|gjets| so that the bound on the blended adjoints sits at 2^(10 - desc->reserved[0]); when the
  * flag comes back the caller repeats the call with reserved[0] += 6 (more headroom, less precision for tiny
@@ -181,8 +183,8 @@ int64_t stpde_backward_chunk_points(const stpde_desc_t *desc, size_t workspace_b
 int stpde_jet_backward(const stpde_desc_t *desc, const float *grid, const int64_t *grid_strides,
                        const float *q, const int64_t *q_strides, const float *const *W,
                        const float *const *B, const float *gy, const float *gjets, float *const *gW,
-                       float *const *gB, float *ggrid, void *workspace, size_t workspace_bytes,
-                       int32_t reuse_forward, int32_t *status, void *stream);
+                       float *const *gB, float *ggrid, float *gbeta, void *workspace,
+                       size_t workspace_bytes, int32_t reuse_forward, int32_t *status, void *stream);
 
 /*
  * Training forward: same outputs as stpde_jet_forward (tensor-core arithmetic), but every operand plane and

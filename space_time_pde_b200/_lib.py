@@ -124,7 +124,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.stpde_jet_backward.restype = c_int
     lib.stpde_jet_backward.argtypes = [descp, c_void_p, i64p, c_void_p, i64p, ctypes.POINTER(c_void_p),
                                        ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
-                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, i32, c_void_p, c_void_p]
+                                       ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_size_t, i32, c_void_p,
+                                       c_void_p]
     lib.stpde_backward_chunk_points.restype = ctypes.c_int64
     lib.stpde_backward_chunk_points.argtypes = [descp, c_size_t]
     lib.stpde_jet_forward_train.restype = c_int

@@ -326,7 +326,7 @@ enum { kBwdFull = 0, kBwdForwardOnly = 1, kBwdReuse = 2 };
 //      kBwdReuse       : reverse sweep on the planes a kBwdForwardOnly call left in the SAME workspace
 static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const float* grid, const float* q,
                         const float* const* W, const float* const* B, const float* gy, const float* gjets,
-                        float* const* gW, float* const* gB, float* ggrid, float* y, float* jets, char* ws,
+                        float* const* gW, float* const* gB, float* ggrid, float* gbeta, float* y, float* jets, char* ws,
                         size_t ws_bytes, int* status, cudaStream_t st) {
     const int dim = d->dim, kc = P.spec.kc, L = P.n_layers - 1;
     if (mode != kBwdForwardOnly) {
@@ -335,6 +335,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
             CUDA_TRY(cudaMemsetAsync(gB[l], 0, (size_t)P.widths[l] * sizeof(float), st));
         }
         if (ggrid) CUDA_TRY(cudaMemsetAsync(ggrid, 0, (size_t)P.nvert_total * d->channels * sizeof(float), st));
+        if (gbeta) CUDA_TRY(cudaMemsetAsync(gbeta, 0, sizeof(float), st));
     }
     if (P.total_pts == 0) return STPDE_OK;
     int64_t pc = bwd_chunk_points(P, ws_bytes);
@@ -431,14 +432,14 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
             a.out_hi = TL.zb[0]; a.out_lo = TL.zb[1];
             a.g_vb = g_vb;
             a.g_wx = gW[L - 1] + P.kh[L - 1]; a.g_wx_ld = P.in_features[L - 1];
-            a.g_wlast = gW[L]; a.g_blast = gB[L];
+            a.g_wlast = gW[L]; a.g_blast = gB[L]; a.g_beta = gbeta;
             a.status = status;
             ProfScope ps(kSlotBwdBlend, st);
             rc = launch_blend_backward(P.spec, a, st);
             if (rc) return fail(rc, "blend_backward: decoder too wide for the shared-memory staging");
         }
         rc = tc_bwd_backward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, P.in_features, Wx,
-                                   gW, g_vb, st);
+                                   gW, g_vb, gbeta, st);
         if (rc) return fail(rc, "%s", tc_last_error());
     }
     if (mode != kBwdForwardOnly) {
@@ -456,6 +457,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
             launch_scale_buffer(gW[l], (int64_t)P.widths[l] * P.in_features[l], scale, st);
             launch_scale_buffer(gB[l], P.widths[l], scale, st);
         }
+        if (gbeta) launch_scale_buffer(gbeta, 1, scale, st);
     }
     CUDA_TRY(cudaGetLastError());
     return STPDE_OK;
@@ -542,14 +544,14 @@ int stpde_jet_forward_train(const stpde_desc_t* desc, const float* grid, const i
     if (P.n_layers < 3) return fail(STPDE_EUNSUPPORTED, "the training forward needs at least 3 linear layers");
     if (!grid || !q || !W || !B || !y || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
     if (P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
-    return run_backward(kBwdForwardOnly, P, desc, grid, q, W, B, nullptr, nullptr, nullptr, nullptr, nullptr, y, jets,
+    return run_backward(kBwdForwardOnly, P, desc, grid, q, W, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, y, jets,
                         (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
 }
 
 int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_t* grid_strides, const float* q,
                        const int64_t* q_strides, const float* const* W, const float* const* B, const float* gy,
-                       const float* gjets, float* const* gW, float* const* gB, float* ggrid, void* workspace,
-                       size_t workspace_bytes, int32_t reuse_forward, int32_t* status, void* stream) {
+                       const float* gjets, float* const* gW, float* const* gB, float* ggrid, float* gbeta,
+                       void* workspace, size_t workspace_bytes, int32_t reuse_forward, int32_t* status, void* stream) {
     Plan P;
     int rc = make_plan(P, desc, grid_strides, q_strides);
     if (rc) return rc;
@@ -558,8 +560,8 @@ int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_
     if (P.spec.kc > 1 && !gjets) return fail(STPDE_EINVAL, "gjets required when derivatives were requested");
     for (int l = 0; l < P.n_layers; ++l)
         if (!W[l] || !B[l] || !gW[l] || !gB[l]) return fail(STPDE_EINVAL, "null weight / gradient pointer for layer %d", l);
-    return run_backward(reuse_forward ? kBwdReuse : kBwdFull, P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, nullptr,
-                        nullptr, (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
+    return run_backward(reuse_forward ? kBwdReuse : kBwdFull, P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, gbeta,
+                        nullptr, nullptr, (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
 }
 
 int stpde_jet_forward_host(const stpde_desc_t* desc, const float* grid, const float* q, const float* const* W,

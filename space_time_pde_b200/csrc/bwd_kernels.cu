@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
 
     // ---- phase 2: (local row, feature) items ----
     const int64_t zplane = (int64_t)a.rows * a.ldz, aplane = (int64_t)a.rows * Kp, oplane = (int64_t)a.rows * ldo;
-    float amax = 0.f;
+    const bool swish_beta = a.act == STPDE_ACT_SWISH && a.g_beta != nullptr;
+    float amax = 0.f, bsum = 0.f;
     for (int e = threadIdx.x; e < 128 * ldo; e += blockDim.x) {
         const int f = e % ldo, lr = e / ldo;
         const int r = row0 + lr;
@@ -180,6 +181,24 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
             float s1, s2, s3;
             act_d123_fast(a.act, a.beta, z[0], s1, s2, s3);
             jet_act_backward<KC>(spec, s1, s2, s3, z, ab, zb);
+            if (swish_beta) {
+                float u = 0.f, w3 = 0.f, sb0, sb1, sb2;
+#pragma unroll
+                for (int c = 1; c < KC; ++c) {
+                    u = fmaf(ab[c], z[c], u);
+                    float za = 0.f, zp = 0.f;
+#pragma unroll
+                    for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                        if (1 + k < KC) {
+                            za = fmaf(spec.sel_a[c][k], z[1 + k], za);
+                            zp = fmaf(spec.sel_b[c][k], z[1 + k], zp);
+                        }
+                    }
+                    w3 = fmaf(ab[c] * za, zp, w3);
+                }
+                swish_dbeta(a.beta, z[0], sb0, sb1, sb2);
+                bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
+            }
             const int vrow = a.cb.vtx[r];
             atomicAdd(a.g_vb + (int64_t)vrow * a.ncat + a.cat_off + f, zb[0]);
             for (int k = 0; k < dim; ++k) {
@@ -204,6 +223,10 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
         }
     }
     if (!(amax < 65000.f)) atomicOr(a.status, kStatusRange);
+    if (swish_beta) {
+        for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.g_beta, bsum);
+    }
     for (int e = threadIdx.x; e < 128 * O; e += blockDim.x) {
         if (row0 + e / O < a.rows) atomicAdd(gB + e % O, ob[e]);      // component 0 only: the bias enters the value
     }

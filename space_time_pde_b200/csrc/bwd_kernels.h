@@ -27,6 +27,7 @@ struct BlendBwdArgs {
     int g_wx_ld;
     float* g_wlast;         // [O][n_feat]
     float* g_blast;         // [O]
+    float* g_beta;          // adjoint of the Swish beta (may be null)
     int* status;
 };
 

@@ -193,6 +193,20 @@ __device__ __forceinline__ void act_d123_fast(int kind, float beta, float z, flo
     }
 }
 
+// Swish x * sigmoid(beta x): partial derivatives of sigma, sigma', sigma'' w.r.t. the learnable beta at fixed z
+// (reference src/nonlinearities.py:5-13 makes beta an nn.Parameter, so loss.backward() needs its gradient):
+//   d loss / d beta += ab_0 sb0 + sb1 sum_{c>=1} ab_c z_c + sb2 sum_{second order c} ab_c z_a z_b
+__device__ __forceinline__ void swish_dbeta(float beta, float z, float& sb0, float& sb1, float& sb2) {
+    const float bz = beta * z;
+    const float s = __fdividef(1.f, 1.f + __expf(-bz));
+    const float ds = s * (1.f - s);
+    const float m = 1.f - 2.f * s;
+    const float t = 2.f + bz * m;
+    sb0 = z * z * ds;
+    sb1 = z * ds * t;
+    sb2 = ds * (t * (1.f + bz * m) + bz * m - 2.f * bz * bz * ds);
+}
+
 // Reverse-mode sweep through the jet activation of one (row, feature):
 //   forward   o_0 = s0(z_0),  o_k = s1 z_k (first order),  o_c = s2 z_a z_b + s1 z_c (second order, parents a, b)
 //   backward  zb_c = d loss / d z_c  from  ob_c = d loss / d o_c

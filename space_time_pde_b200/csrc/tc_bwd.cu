@@ -237,7 +237,7 @@ static int launch_wgrad(const TcBwdContext& tc, const TcBwdLayer& L, float* gW, 
 
 int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                           const float* Vb, int ncat, const int* cat_off, const int* in_features, const float* const* Wx,
-                          float* const* gW, float* g_vb, cudaStream_t st) {
+                          float* const* gW, float* g_vb, float* g_beta, cudaStream_t st) {
     for (int l = tc.n_layers - 2; l >= 1; --l) {
         const TcBwdLayer& L = tc.layer[l];
         {
@@ -256,6 +256,7 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         a.wscale = tc.wscale + l;
         a.Wx = Wx[l - 1];
         a.g_vb = g_vb;
+        a.g_beta = g_beta;
         const int kh_below = l >= 2 ? tc.layer[l - 1].kh : 0;      // activation columns of layer l-1's weight
         a.g_wx = gW[l - 1] + kh_below;
         a.g_wx_ld = in_features[l - 1];

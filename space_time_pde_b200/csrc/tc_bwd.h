@@ -54,7 +54,7 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
 // gW[l] : gradient of layer l's weight [widths[l]][in_features[l]] (scaled by S), g_vb [nvert][ncat]
 int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                           const float* Vb, int ncat, const int* cat_off, const int* in_features, const float* const* Wx,
-                          float* const* gW, float* g_vb, cudaStream_t st);
+                          float* const* gW, float* g_vb, float* g_beta, cudaStream_t st);
 
 // launch wrappers instantiated in tc_bwd_a/b/c.cu (one translation unit per kernel mode)
 int tc_launch_pair_save(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,

@@ -189,6 +189,7 @@ struct LayerArgs {
     float* g_vb;           // MODE 2/3: adjoint of Vb, [nvert][ncat] (atomics)
     float* g_wx;           // MODE 2/3: adjoint of the coordinate columns, &gW[0][kh], row stride g_wx_ld (atomics)
     int g_wx_ld;
+    float* g_beta;         // MODE 2/3: adjoint of the Swish beta (atomics), may be null
     uint32_t wait_ns;      // suspend-time hint of the mbarrier waits (pair kernel)
 };
 
@@ -729,6 +730,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         const int64_t plane = (int64_t)args.rows * args.ld_out;
         const int64_t zplane = (int64_t)args.rows * args.ldz;
         const int n_first = spec.n_first;
+        const bool swish_beta = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
@@ -738,6 +740,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             const int g = f0 + quarter * 32 + lane;
             const bool g_store = g < args.n_store;
             const bool g_ok = g < args.n_feat;
+            float bsum = 0.f;                                       // Swish only: d loss / d beta of this thread's elements
             float G[kMaxDim], A[KC];                                // per-tile partial sums of the coordinate-column adjoint
 #pragma unroll
             for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
@@ -858,6 +861,11 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
                             zb[0] = z0b;
+                            if (swish_beta) {
+                                float sb0, sb1, sb2;
+                                swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
+                                bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
+                            }
 #pragma unroll
                             for (int k = 0; k < STPDE_MAX_FIRST; ++k)
                                 if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
@@ -887,6 +895,11 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                                 else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
+                            if (swish_beta) {
+                                float sb0, sb1, sb2;
+                                swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
+                                bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
+                            }
                         }
 #pragma unroll
                         for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
@@ -922,6 +935,10 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
 #pragma unroll
                 for (int k = 0; k < kMaxDim; ++k)
                     if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
+            }
+            if (swish_beta) {
+                for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+                if (lane == 0) atomicAdd(args.g_beta, bsum);
             }
             if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
             tc_fence_before();

@@ -254,7 +254,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
                  Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
                  spec: JetSpec, precision: str, gy: torch.Tensor, gjets: Optional[torch.Tensor],
                  need_grid: bool = True, check: bool = True, stash_token: int = 0):
-    """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l]).
+    """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l]); the gradient of the
+    Swish beta is left in ``raw_backward.last_gbeta`` (a 1-element tensor, zero for other activations).
 
     ``stash_token``: token of the training forward whose planes may still sit in the device's stash workspace; if it
     is still current the forward is not recomputed.
@@ -275,6 +276,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
     gB = [torch.empty_like(v) for v in Bc]
     ggrid = torch.empty(grid.shape, dtype=torch.float32, device=device) if need_grid else None
     status = torch.zeros(1, dtype=torch.int32, device=device)
+    gbeta = torch.zeros(1, dtype=torch.float32, device=device)
+    raw_backward.last_gbeta = gbeta
     wptr = (ctypes.c_void_p * len(Wc))(*[w.data_ptr() for w in Wc])
     bptr = (ctypes.c_void_p * len(Bc))(*[v.data_ptr() for v in Bc])
     gwptr = (ctypes.c_void_p * len(gW))(*[w.data_ptr() for w in gW])
@@ -298,8 +301,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
             status.zero_()
             rc = lib.stpde_jet_backward(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr, bptr,
                                         gy.data_ptr(), gjets.data_ptr() if spec.n_jet else None, gwptr, gbptr,
-                                        ggrid.data_ptr() if ggrid is not None else None, ws.data_ptr(), ws.numel(),
-                                        reuse, status.data_ptr(), stream)
+                                        ggrid.data_ptr() if ggrid is not None else None, gbeta.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), reuse, status.data_ptr(), stream)
             _lib.check(rc)
             if not sync or not (int(status.item()) & 2):
                 break
@@ -310,10 +313,10 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
 
 
 def fused_backward_supported(q: torch.Tensor, spec: JetSpec, n_layers: int, needs_q: bool, needs_beta: bool) -> bool:
-    """The CUDA reverse sweep covers grid / weight / bias gradients of decoders with >= 3 linear layers."""
+    """The CUDA reverse sweep covers grid / weight / bias / Swish-beta gradients of decoders with >= 3 linear layers."""
     if os.environ.get("STPDE_BACKWARD", "fused") == "torch":
         return False
-    return (q.is_cuda and n_layers >= 3 and not needs_q and not needs_beta
+    return (q.is_cuda and n_layers >= 3 and not needs_q
             and 1 + len(spec.first) + len(spec.second) <= _lib.MAX_COMPONENTS)
 
 
@@ -321,7 +324,7 @@ class FusedJetQuery(torch.autograd.Function):
     """(grid, q, *params) -> (y, jets).
 
     Backward: ``stpde_jet_backward`` (fused CUDA reverse sweep) for the gradients w.r.t. the latent grid and the
-    decoder weights / biases; gradients w.r.t. the query points or a learnable Swish beta (not needed by the
+    decoder weights / biases / the learnable Swish beta; gradients w.r.t. the query points (not needed by the
     reference training loop) re-evaluate the jets with differentiable torch ops (see _torch_jets.py)."""
 
     @staticmethod
@@ -363,6 +366,8 @@ class FusedJetQuery(torch.autograd.Function):
                                          bprec, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
             if needs[0]:
                 result[0] = ggrid
+            if has_beta and needs[5]:
+                result[5] = raw_backward.last_gbeta.reshape(beta_t.shape).to(beta_t.dtype)
             for i, g in enumerate(list(gW) + list(gB)):
                 if needs[9 + i]:
                     result[9 + i] = g.to(params[i].dtype)

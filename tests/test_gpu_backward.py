@@ -43,7 +43,7 @@ def reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj):
     g64 = grid.double().requires_grad_(True)
     W64 = [w.double().requires_grad_(True) for w in Ws]
     b64 = [b.double().requires_grad_(True) for b in bs]
-    beta_t = torch.tensor(beta, dtype=torch.float64, device=grid.device)
+    beta_t = torch.tensor(beta, dtype=torch.float64, device=grid.device, requires_grad=(act == "swish"))
     grads = None
     p = q.shape[1]
     step = 512                                           # bounded autograd tape
@@ -53,11 +53,13 @@ def reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj):
         loss = (y * gy[:, sl].double()).sum()
         if j is not None:
             loss = loss + (j * gj[:, :, sl].double()).sum()
-        gs = torch.autograd.grad(loss, [g64] + W64 + b64, allow_unused=True)
-        gs = [torch.zeros_like(t) if g is None else g for g, t in zip(gs, [g64] + W64 + b64)]
+        leaves = [g64] + W64 + b64 + ([beta_t] if act == "swish" else [])
+        gs = torch.autograd.grad(loss, leaves, allow_unused=True)
+        gs = [torch.zeros_like(t) if g is None else g for g, t in zip(gs, leaves)]
         grads = gs if grads is None else [a + b for a, b in zip(grads, gs)]
     n = len(Ws)
-    return grads[0], grads[1:1 + n], grads[1 + n:]
+    reference_grads.last_gbeta = float(grads[1 + 2 * n]) if act == "swish" else None
+    return grads[0], grads[1:1 + n], grads[1 + n:1 + 2 * n]
 
 
 def run_case(dev, d, gshape, c, o, nf, act, first, second, p, precision, seed=0, beta=1.0, gscale=1.0):
@@ -71,8 +73,11 @@ def run_case(dev, d, gshape, c, o, nf, act, first, second, p, precision, seed=0,
     lo, hi = jets.bounds_tensors(0., 1., d, dev)
     ggrid, gW, gB = jets.raw_backward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, gy, gj)
     torch.cuda.synchronize()
+    gbeta = float(jets.raw_backward.last_gbeta)
     rgrid, rW, rB = reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj)
     errs = {"grid": rel_linf(ggrid.cpu().numpy(), rgrid.cpu().numpy())}
+    if act == "swish":
+        errs["beta"] = abs(gbeta - reference_grads.last_gbeta) / max(abs(reference_grads.last_gbeta), 1e-30)
     for l in range(len(Ws)):
         kh = 0 if l == 0 else Ws[l - 1].shape[0]
         a, b = gW[l].cpu().numpy(), rW[l].cpu().numpy()
@@ -334,5 +339,30 @@ def test_encoder_gradients_through_permuted_latent_grid(dev, monkeypatch):
         return [enc.weight.grad.clone(), enc.bias.grad.clone(), model.fc[0].weight.grad.clone()]
 
     fused, ref = grads("fused"), grads("torch")
+    for a, b in zip(fused, ref):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+def test_swish_beta_gradient_through_module(dev, monkeypatch):
+    """The learnable beta of the reference's Swish (src/nonlinearities.py:5-13) gets its gradient from the fused sweep."""
+    torch.manual_seed(12)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["swish"]).to(dev)
+    with torch.no_grad():
+        model.activ.beta.fill_(1.2)
+    grid0 = (torch.randn(1, 4, 6, 5, 16) * 0.5).to(dev)
+    q = torch.rand(1, 1200, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+
+    def grads(route):
+        monkeypatch.setenv("STPDE_BACKWARD", route)
+        grid = grid0.clone().requires_grad_(True)
+        model.zero_grad()
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        y, res = layer(q, return_residue=True)
+        (y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()).backward()
+        return [model.activ.beta.grad.clone().reshape(1), grid.grad.clone(), model.fc[2].weight.grad.clone()]
+
+    fused, ref = grads("fused"), grads("torch")
+    assert fused[0].abs().item() > 0
     for a, b in zip(fused, ref):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
