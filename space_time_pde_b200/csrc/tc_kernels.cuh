@@ -357,6 +357,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                 float zs_next[8];
                 if (rb + kEpiPerQuarter < NRB) load_skip(r0 + (rb + kEpiPerQuarter) * 8, g, wx, zs_next);
                 tmem_wait_ld();
+                dispatch_act(args.act, [&](auto act_c) {
+                constexpr int kAct = decltype(act_c)::value;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = r0 + rb * 8 + i;
@@ -364,7 +366,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
 #pragma unroll
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
-                    act_jet_fast(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    act_jet_fast(kAct, args.beta, zt[0] + zs[i], s0, s1, s2);
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;
@@ -404,6 +406,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                         }
                     }
                 }
+                });
 #pragma unroll
                 for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
             }
@@ -730,7 +733,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         const int64_t plane = (int64_t)args.rows * args.ld_out;
         const int64_t zplane = (int64_t)args.rows * args.ldz;
         const int n_first = spec.n_first;
-        const bool swish_beta = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
+        const bool swish_beta_rt = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
@@ -821,6 +824,8 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                         fetch(rbase, zc);
                     }
                     tmem_wait_ld();
+                    dispatch_act(args.act, [&](auto act_c) {
+                    constexpr int kAct = decltype(act_c)::value;
 #pragma unroll
                     for (int j = 0; j < H; ++j) {
                         const int r = rbase + j;
@@ -834,7 +839,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
 #pragma unroll
                         for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
                         float s1, s2, s3, z0b;
-                        act_d123_fast(args.act, args.beta, zc[0][j], s1, s2, s3);
+                        act_d123_fast(kAct, args.beta, zc[0][j], s1, s2, s3);
                         if constexpr (MODE == kModeBwd) {
                             float zb[KC], cross[STPDE_MAX_FIRST];
 #pragma unroll
@@ -861,7 +866,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
                             zb[0] = z0b;
-                            if (swish_beta) {
+                            if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
                                 float sb0, sb1, sb2;
                                 swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
                                 bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
@@ -895,7 +900,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                                 else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
-                            if (swish_beta) {
+                            if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
                                 float sb0, sb1, sb2;
                                 swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
                                 bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
@@ -905,6 +910,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                         for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
                         if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
                     }
+                    });
                     if constexpr (kPrefetch) {
 #pragma unroll
                         for (int c = 0; c < PC; ++c)
@@ -936,7 +942,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 for (int k = 0; k < kMaxDim; ++k)
                     if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
             }
-            if (swish_beta) {
+            if (swish_beta_rt) {
                 for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
                 if (lane == 0) atomicAdd(args.g_beta, bsum);
             }
@@ -998,6 +1004,8 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 float zs_next[8];
                 if (rb + kEpiPQ < NRB) load_skip(r0 + (rb + kEpiPQ) * 8, g, wx, zs_next);
                 tmem_wait_ld();
+                dispatch_act(args.act, [&](auto act_c) {
+                constexpr int kAct = decltype(act_c)::value;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = r0 + rb * 8 + i;
@@ -1005,7 +1013,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
 #pragma unroll
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
-                    act_jet_fast(args.act, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    act_jet_fast(kAct, args.beta, zt[0] + zs[i], s0, s1, s2);
                     if constexpr (MODE == kModeFwdSave) {
                         if (g < args.n_feat && r < args.rows) {     // pre-activations for the reverse sweep
                             const int64_t zplane = (int64_t)args.rows * args.ldz;
@@ -1054,6 +1062,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                         }
                     }
                 }
+                });
 #pragma unroll
                 for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
             }

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
     float xr[kMaxDim], vb[F];
     const int rbase = blockIdx.y * 64 + rl;
     if (rbase < rows) load_row(rbase, xr, vb);
+    dispatch_act(act, [&](auto act_c) {
+    constexpr int kAct = decltype(act_c)::value;
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
         const int r = rbase + 8 * j;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
             float z = vb[e];
 #pragma unroll
             for (int k = 0; k < kMaxDim; ++k) z = fmaf(wx[e][k], xr[k], z);
-            act_jet_fast(act, beta, z, s0[e], s1[e], s2[e]);
+            act_jet_fast(kAct, beta, z, s0[e], s1[e], s2[e]);
             smax = fmaxf(smax, fmaxf(fabsf(s0[e]), fmaxf(fabsf(s1[e]), fabsf(s2[e]))));
         }
 #pragma unroll
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
 #pragma unroll
         for (int e = 0; e < F; ++e) vb[e] = vb_n[e];
     }
+    });
     if (!(smax * cmax < 65000.f)) atomicOr(status, kStatusRange);
 }
 
