@@ -193,13 +193,20 @@ struct LayerArgs {
     uint32_t wait_ns;      // suspend-time hint of the mbarrier waits (pair kernel)
 };
 
+// Static jet specifications (template parameter SPEC): 0 = generic (runtime JetSpec), 1 = the Rayleigh-Benard set
+// K = 6 with components [value | d/dq_0, d/dq_1, d/dq_2 | d2/dq_1^2, d2/dq_2^2] (parents of component 4 / 5 are
+// component 2 / 3).  With the structure known at compile time the per-row epilogue code is branch-free, so the
+// compiler interleaves the dependent chains of the 8 rows instead of running them one after the other.
+constexpr int kSpecGeneric = 0;
+constexpr int kSpecRb2 = 1;
+
 // kernel modes of tc_layer_pair_kernel
 constexpr int kModeFwd = 0;       // forward layer (inference)
 constexpr int kModeFwdSave = 1;   // forward layer that also stores its pre-activations (recompute pass of the backward)
 constexpr int kModeBwd = 2;       // dgrad of layer l (W_l^T . zbar_l) + reverse jet activation of layer l-1 >= 1
 constexpr int kModeBwd0 = 3;      // dgrad of layer 1 + reverse of the closed-form layer 0
 
-template <int KC>
+template <int KC, int SPEC = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -370,19 +377,25 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;
+                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                        o[1] = s1 * zt[1]; o[2] = s1 * zt[2]; o[3] = s1 * zt[3];
+                        o[4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
+                        o[5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
+                    } else {
 #pragma unroll
-                    for (int c = 1; c < KC; ++c) {
-                        o[c] = s1 * zt[c];
-                        if (c > n_first) {               // second order (warp-uniform): parents za, zb
-                            float za = 0.f, zb = 0.f;
+                        for (int c = 1; c < KC; ++c) {
+                            o[c] = s1 * zt[c];
+                            if (c > n_first) {               // second order (warp-uniform): parents za, zb
+                                float za = 0.f, zb = 0.f;
 #pragma unroll
-                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                if (1 + k < KC) {
-                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                    if (1 + k < KC) {
+                                        za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                        zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                    }
                                 }
+                                o[c] = fmaf(s2 * za, zb, o[c]);
                             }
-                            o[c] = fmaf(s2 * za, zb, o[c]);
                         }
                     }
                     if (g_store && r < args.rows) {
@@ -494,7 +507,7 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
 // planes but GENERATED in shared memory by 8 generator warps from the closed-form layer-0 jets
 // (a_c = sigma^(k)(z0) * coef_c, z0 = Vb0[vertex] + W0x . x_rel), written in the SWIZZLE_128B K-major layout the
 // UMMA descriptors expect.  This removes layer 0's HBM round trip (412 GB / step at BASELINE config 2).
-template <int KC, bool GEN, int MODE = kModeFwd>
+template <int KC, bool GEN, int MODE = kModeFwd, int SPEC = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -841,28 +854,41 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                         float s1, s2, s3, z0b;
                         act_d123_fast(kAct, args.beta, zc[0][j], s1, s2, s3);
                         if constexpr (MODE == kModeBwd) {
-                            float zb[KC], cross[STPDE_MAX_FIRST];
-#pragma unroll
-                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+                            float zb[KC];
                             float u = 0.f, w3 = 0.f;
+                            if constexpr (SPEC == kSpecRb2 && KC == 6) {
 #pragma unroll
-                            for (int c = 1; c < KC; ++c) {
-                                u = fmaf(ab[c], zc[c][j], u);
-                                zb[c] = s1 * ab[c];
-                                if (c > n_first) {                 // second order (warp-uniform): parents za, zp
-                                    float za = 0.f, zp = 0.f;
+                                for (int c = 1; c < KC; ++c) { u = fmaf(ab[c], zc[c][j], u); zb[c] = s1 * ab[c]; }
+                                const float p4 = ab[4] * zc[2][j], p5 = ab[5] * zc[3][j];
+                                w3 = fmaf(p4, zc[2][j], p5 * zc[3][j]);
+                                zb[2] = fmaf(2.f * s2, p4, zb[2]);
+                                zb[3] = fmaf(2.f * s2, p5, zb[3]);
+                            } else {
+                                float cross[STPDE_MAX_FIRST];
 #pragma unroll
-                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                        if (1 + k < KC) {
-                                            za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
-                                            zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+#pragma unroll
+                                for (int c = 1; c < KC; ++c) {
+                                    u = fmaf(ab[c], zc[c][j], u);
+                                    zb[c] = s1 * ab[c];
+                                    if (c > n_first) {                 // second order (warp-uniform): parents za, zp
+                                        float za = 0.f, zp = 0.f;
+#pragma unroll
+                                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                            if (1 + k < KC) {
+                                                za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
+                                                zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
+                                            }
                                         }
-                                    }
-                                    w3 = fmaf(ab[c] * za, zp, w3);
+                                        w3 = fmaf(ab[c] * za, zp, w3);
 #pragma unroll
-                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                                        if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
+                                        for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                            if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
+                                    }
                                 }
+#pragma unroll
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                    if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
                             zb[0] = z0b;
@@ -871,9 +897,6 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                                 swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
                                 bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
                             }
-#pragma unroll
-                            for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                                if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
 #pragma unroll
                             for (int c = 1; c < KC; ++c) A[c] += zb[c];
                             if (g_store && r_ok) {
@@ -893,11 +916,20 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                         } else {
                             // layer 0: a_c = sigma^(order_c)(z0) * cf_c
                             float t1 = 0.f, t2 = 0.f;
+                            if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                                t1 = fmaf(ab[1], cf[1], fmaf(ab[2], cf[2], ab[3] * cf[3]));
+                                t2 = fmaf(ab[4], cf[4], ab[5] * cf[5]);
 #pragma unroll
-                            for (int c = 1; c < KC; ++c) {
-                                const float pc = ab[c] * cf[c];
-                                if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
-                                else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
+                                for (int c = 1; c < 4; ++c) A[c] = fmaf(ab[c], s1, A[c]);
+                                A[4] = fmaf(ab[4], s2, A[4]);
+                                A[5] = fmaf(ab[5], s2, A[5]);
+                            } else {
+#pragma unroll
+                                for (int c = 1; c < KC; ++c) {
+                                    const float pc = ab[c] * cf[c];
+                                    if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
+                                    else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
+                                }
                             }
                             z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
                             if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
@@ -1026,19 +1058,25 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;
+                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                        o[1] = s1 * zt[1]; o[2] = s1 * zt[2]; o[3] = s1 * zt[3];
+                        o[4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
+                        o[5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
+                    } else {
 #pragma unroll
-                    for (int c = 1; c < KC; ++c) {
-                        o[c] = s1 * zt[c];
-                        if (c > n_first) {               // second order (warp-uniform): parents za, zb
-                            float za = 0.f, zb = 0.f;
+                        for (int c = 1; c < KC; ++c) {
+                            o[c] = s1 * zt[c];
+                            if (c > n_first) {               // second order (warp-uniform): parents za, zb
+                                float za = 0.f, zb = 0.f;
 #pragma unroll
-                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                if (1 + k < KC) {
-                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                    if (1 + k < KC) {
+                                        za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                        zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                    }
                                 }
+                                o[c] = fmaf(s2 * za, zb, o[c]);
                             }
-                            o[c] = fmaf(s2 * za, zb, o[c]);
                         }
                     }
                     if (g_store && r < args.rows) {

@@ -25,8 +25,13 @@ int tc_launch_layer_pair_gen(int kc, const TcContext& tc, const TcLayerPlan& L, 
         default: { constexpr int KC = 10; CALL; } break; \
     }
 
+// Rayleigh-Benard jet set [value | d0, d1, d2 | d11, d22] -> kernels specialised at compile time (tc::kSpecRb2)
+static inline bool spec_is_rb2(const JetSpec& s) {
+    return s.kc == 6 && s.n_first == 3 && s.n_second == 2 && s.pa[4] == 2 && s.pb[4] == 2 && s.pa[5] == 3 && s.pb[5] == 3;
+}
+
 #ifdef STPDE_TC_LAUNCH_IMPL
-template <int KC>
+template <int KC, int SPEC = 0>
 static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
                         cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
@@ -36,17 +41,17 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!(configured >> (dev_ & 63) & 1ull)) {
-        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
         configured |= 1ull << (dev_ & 63);
     }
     const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
-    tc::tc_layer_kernel<KC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    tc::tc_layer_kernel<KC, SPEC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
-template <int KC, bool GEN>
+template <int KC, bool GEN, int SPEC = 0>
 static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
                              cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
@@ -55,21 +60,21 @@ static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const Je
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!(configured >> (dev_ & 63) & 1ull)) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN, tc::kModeFwd, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
         configured |= 1ull << (dev_ & 63);
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = tc.num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, GEN><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    tc::tc_layer_pair_kernel<KC, GEN, tc::kModeFwd, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
 // CTA-pair kernel in one of the training modes (tc_kernels.cuh kMode*): the maps are passed explicitly because the
 // reverse sweep runs the same kernel on W^T / zbar planes.  Always the pair kernel: TMA zero-fills the feature
 // rows beyond the layer width.
-template <int KC, int MODE>
+template <int KC, int MODE, int SPEC = 0>
 static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
                                   const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
@@ -78,14 +83,14 @@ static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CU
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!(configured >> (dev_ & 63) & 1ull)) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, false, MODE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel, training mode) failed");
         configured |= 1ull << (dev_ & 63);
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, false, MODE><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    tc::tc_layer_pair_kernel<KC, false, MODE, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
     return STPDE_OK;
 }
 
