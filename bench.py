@@ -404,70 +404,80 @@ def main():
     #      and the decoder weights, then ONE all-reduce of [loss sums | counts | flat gradients] ----
     train = None
     if args.train_steps > 0:
-        from space_time_pde_b200.parallel import StepReducer
-        grid_t = grid.clone().requires_grad_(True)
-        params = [grid_t] + list(model.parameters())
-        for p_ in params[1:]:
-            p_.requires_grad_(True)
-        reducer = StepReducer(params)
-        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid_t, pts, 0., 1.))
+        try:
+            from space_time_pde_b200.parallel import StepReducer
+            grid_t = grid.clone().requires_grad_(True)
+            params = [grid_t] + list(model.parameters())
+            for p_ in params[1:]:
+                p_.requires_grad_(True)
+            reducer = StepReducer(params)
+            layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid_t, pts, 0., 1.))
 
-        # Points are independent, so the step walks the batch in chunks that fit the training stash (the forward of
-        # a chunk leaves its operand planes in the workspace and the chunk's backward reuses them: no recompute);
-        # gradients accumulate in .grad across chunks exactly as one big backward would.
-        os.environ["STPDE_WORKSPACE_MB"] = str(args.train_workspace_mb)
-        jets.release_workspaces()
-        jets.set_backward_precision(args.train_backward_precision)
-        tchunk = args.train_chunk
+            # Points are independent, so the step walks the batch in chunks that fit the training stash (the forward of
+            # a chunk leaves its operand planes in the workspace and the chunk's backward reuses them: no recompute);
+            # gradients accumulate in .grad across chunks exactly as one big backward would.
+            os.environ["STPDE_WORKSPACE_MB"] = str(args.train_workspace_mb)
+            jets.release_workspaces()
+            jets.set_backward_precision(args.train_backward_precision)
+            tchunk = args.train_chunk
 
-        def train_step():
+            def train_step():
+                for p_ in params:
+                    p_.grad = None
+                reg_sum = torch.zeros((), device=device)
+                pde_sum = torch.zeros((), device=device)
+                for s0 in range(0, NPTS, tchunk):
+                    y, res = layer(q[:, s0:s0 + tchunk], return_residue=True)
+                    reg = y.abs().sum()
+                    pde = torch.stack(list(res.values())).abs().sum()
+                    (reg / (world * 4 * NPTS) + 0.0125 * pde / (world * 4 * NPTS)).backward()
+                    reg_sum += reg.detach()
+                    pde_sum += pde.detach()
+                return reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": 4 * NPTS, "pde": 4 * NPTS})
+
+            train_step()
+            barrier()
+            lib.stpde_profile_enable(1)
+            _lib.profile_read()
+            tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tv0.record()
+            for _ in range(args.train_steps):
+                means = train_step()
+            tv1.record()
+            barrier()
+            prof_t = _lib.profile_read()
+            lib.stpde_profile_enable(0)
+            tms = torch.tensor([tv0.elapsed_time(tv1)], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            tms = float(tms.item()) / args.train_steps
+            # algorithmic FLOPs of a training step = 3 x the forward contractions (forward, dgrad, wgrad); the recompute
+            # of the forward inside the backward is overhead, not counted
+            train = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
+                     "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
+                     "backward_precision": args.precision if args.train_backward_precision == "same" else args.train_backward_precision,
+                     "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients), "
+                             "chunks of the batch with the forward planes kept for the backward (no recompute)"
+                             + (" + one NCCL all-reduce of the flat gradient buffer" if world > 1 else ""),
+                     "algorithmic_tflops": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12,
+                     "frac_of_peak": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12 / peaks["tflops"],
+                     "loss_reg": float(means["reg"]), "loss_pde": float(means["pde"]),
+                     "kernel_ms_per_step": {k: v[0] / args.train_steps for k, v in prof_t.items() if v[1] > 0},
+                     "gpu_launches_per_step": int(sum(v[1] for v in prof_t.values()) / args.train_steps)}
             for p_ in params:
                 p_.grad = None
-            reg_sum = torch.zeros((), device=device)
-            pde_sum = torch.zeros((), device=device)
-            for s0 in range(0, NPTS, tchunk):
-                y, res = layer(q[:, s0:s0 + tchunk], return_residue=True)
-                reg = y.abs().sum()
-                pde = torch.stack(list(res.values())).abs().sum()
-                (reg / (world * 4 * NPTS) + 0.0125 * pde / (world * 4 * NPTS)).backward()
-                reg_sum += reg.detach()
-                pde_sum += pde.detach()
-            return reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": 4 * NPTS, "pde": 4 * NPTS})
-
-        train_step()
-        barrier()
-        lib.stpde_profile_enable(1)
-        _lib.profile_read()
-        tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tv0.record()
-        for _ in range(args.train_steps):
-            means = train_step()
-        tv1.record()
-        barrier()
-        prof_t = _lib.profile_read()
-        lib.stpde_profile_enable(0)
-        tms = torch.tensor([tv0.elapsed_time(tv1)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        tms = float(tms.item()) / args.train_steps
-        # algorithmic FLOPs of a training step = 3 x the forward contractions (forward, dgrad, wgrad); the recompute
-        # of the forward inside the backward is overhead, not counted
-        train = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
-                 "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
-                 "backward_precision": args.precision if args.train_backward_precision == "same" else args.train_backward_precision,
-                 "what": "values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder gradients), "
-                         "chunks of the batch with the forward planes kept for the backward (no recompute)"
-                         + (" + one NCCL all-reduce of the flat gradient buffer" if world > 1 else ""),
-                 "algorithmic_tflops": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12,
-                 "frac_of_peak": 3.0 * NPTS * fpt / (tms * 1e-3) / 1e12 / peaks["tflops"],
-                 "loss_reg": float(means["reg"]), "loss_pde": float(means["pde"]),
-                 "kernel_ms_per_step": {k: v[0] / args.train_steps for k, v in prof_t.items() if v[1] > 0},
-                 "gpu_launches_per_step": int(sum(v[1] for v in prof_t.values()) / args.train_steps)}
-        for p_ in params:
-            p_.grad = None
-        jets.release_workspaces()
-        jets.set_backward_precision("same")
-        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+            jets.release_workspaces()
+            jets.set_backward_precision("same")
+            layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        except Exception as exc:   # the headline metric must survive a failing optional leg (e.g. out of memory)
+            if world > 1:
+                raise
+            train = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            lib.stpde_profile_enable(0)
+            jets.release_workspaces()
+            jets.set_backward_precision("same")
+            layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        os.environ.pop("STPDE_WORKSPACE_MB", None)
 
     if world > 1:
         dist.barrier()

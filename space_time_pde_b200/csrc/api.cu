@@ -380,13 +380,15 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
     float* scale = (float*)(ws + P.off_bwd_scale + 256);
     const float* Wx[kMaxLayers] = {nullptr};
     prof_begin(kSlotSetup, st);
+    const bool prep = mode != kBwdReuse;     // kBwdReuse: the training forward left all of this in the workspace
     for (int l = 0; l < P.n_layers; ++l) {
         float* wx = l < L ? (float*)(ws + P.off_wx[l]) : nullptr;
         Wx[l] = wx;
+        if (!prep) continue;
         if (l == L) launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, P.widths[l], P.kp[l], (float*)(ws + P.off_wh[l]), nullptr, st);
         else launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, 0, 1, nullptr, wx, st);
     }
-    launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
+    if (prep) launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
     CUDA_TRY(cudaMemsetAsync(g_vb, 0, (size_t)P.nvert_total * P.ncat * sizeof(float), st));
     if (mode != kBwdForwardOnly) {
         // reserved[0] = headroom bits below the default adjoint scale (the binding retries with more headroom when
@@ -399,7 +401,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
 
     TcBwdContext tc;
     int rc = tc_bwd_prepare(tc, d->precision, P.n_layers, P.widths, P.in_features, W, ws + P.off_tc, tc_chunk,
-                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, st);
+                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, prep, st);
     if (rc) return fail(rc, "%s", tc_last_error());
 
     const TcBwdLayer& TL = tc.layer[P.n_layers - 2];

@@ -51,7 +51,7 @@ size_t tc_bwd_per_point_bytes(int n_layers, const int* widths, int kc, int ncorn
 // ---------------------------------------------------------------------------------------------
 int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                    const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-                   int* status, cudaStream_t st) {
+                   int* status, bool split_weights, cudaStream_t st) {
     if (!tc_encode_available()) return tc_fail(STPDE_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
     if (n_layers < 3) return tc_fail(STPDE_EUNSUPPORTED, "the tensor-core backward needs at least one hidden contraction");
     if (rows % tc::kWgKBlock) return tc_fail(STPDE_EINVAL, "chunk rows must be a multiple of 64");
@@ -66,7 +66,7 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
     cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
     tc.wscale = (float*)fixed_ws;
     tc.absmax = (unsigned*)(fixed_ws + 512);
-    cudaMemsetAsync(tc.absmax, 0, 256, st);
+    if (split_weights) cudaMemsetAsync(tc.absmax, 0, 256, st);
     tc.ld0 = round_up(widths[0], 64);
     tc.n0 = widths[0];
 
@@ -106,9 +106,11 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
         L.w_lo_ptr = (__half*)(fixed_ws + off); off += w_plane;
         L.wt_hi_ptr = (__half*)(fixed_ws + off); off += wt_plane;
         L.wt_lo_ptr = (__half*)(fixed_ws + off); off += wt_plane;
-        tc_launch_split_weights(W[l], widths[l], in_features[l], L.kh, np256, L.ld_in, tc.absmax + l, tc.wscale + l,
-                                L.w_hi_ptr, L.w_lo_ptr, st);
-        launch_split_weights_t(W[l], widths[l], in_features[l], L.kh, fp256, L.ldz, tc.absmax + l, L.wt_hi_ptr, L.wt_lo_ptr, st);
+        if (split_weights) {     // (a backward that reuses the training forward's workspace finds them in place)
+            tc_launch_split_weights(W[l], widths[l], in_features[l], L.kh, np256, L.ld_in, tc.absmax + l, tc.wscale + l,
+                                    L.w_hi_ptr, L.w_lo_ptr, st);
+            launch_split_weights_t(W[l], widths[l], in_features[l], L.kh, fp256, L.ldz, tc.absmax + l, L.wt_hi_ptr, L.wt_lo_ptr, st);
+        }
         for (int h = 0; h < 2; ++h) {
             L.a_in[h] = a_planes[l - 1][h];
             L.a_out[h] = L.last ? nullptr : a_planes[l][h];

@@ -42,7 +42,7 @@ size_t tc_bwd_per_point_bytes(int n_layers, const int* widths, int kc, int ncorn
 
 int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                    const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-                   int* status, cudaStream_t st);
+                   int* status, bool split_weights, cudaStream_t st);
 
 // forward recompute of one chunk: layer 0 + hidden layers, all operand planes and pre-activations kept;
 // act_last = fp32 activations of the last hidden layer [kc][rows][np_last]

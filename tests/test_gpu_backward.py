@@ -366,3 +366,19 @@ def test_swish_beta_gradient_through_module(dev, monkeypatch):
     assert fused[0].abs().item() > 0
     for a, b in zip(fused, ref):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+def test_backward_empty_and_tiny_batches(dev):
+    """Edge cases of the point dimension: p = 0 (all gradients exactly zero) and p = 1."""
+    gen = torch.Generator().manual_seed(13)
+    d, c, o, nf = 3, 16, 4, 8
+    Ws, bs = make_decoder(gen, d, c, o, nf, dev)
+    grid = (torch.randn(1, 3, 4, 5, c, generator=gen) * 0.5).to(dev)
+    spec = JetSpec(*RB2)
+    lo, hi = jets.bounds_tensors(0., 1., d, dev)
+    q0 = torch.empty(1, 0, d, device=dev)
+    ggrid, gW, gB = jets.raw_backward(grid, q0, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3",
+                                      torch.empty(1, 0, o, device=dev), torch.empty(spec.n_jet, 1, 0, o, device=dev))
+    assert ggrid.abs().max() == 0 and all(g.abs().max() == 0 for g in gW + gB)
+    errs = run_case(dev, d, (3, 4, 5), c, o, nf, "softplus", *RB2, p=1, precision="fp16x3", seed=14)
+    assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
