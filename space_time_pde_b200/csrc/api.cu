@@ -519,8 +519,9 @@ int stpde_jet_forward(const stpde_desc_t* desc, const float* grid, const int64_t
     Plan P;
     int rc = make_plan(P, desc, grid_strides, q_strides);
     if (rc) return rc;
-    if (!grid || !q || !W || !B || !y || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
-    if (P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
+    const bool empty = P.total_pts == 0;      // empty batches come with null data pointers (torch.empty(0).data_ptr() == 0)
+    if (!grid || !W || !B || !workspace || !status || (!empty && (!q || !y))) return fail(STPDE_EINVAL, "null pointer argument");
+    if (!empty && P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
     return run_forward(P, desc, grid, q, W, B, y, jets, (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
 }
 
@@ -544,8 +545,9 @@ int stpde_jet_forward_train(const stpde_desc_t* desc, const float* grid, const i
     int rc = make_plan(P, desc, grid_strides, q_strides);
     if (rc) return rc;
     if (P.n_layers < 3) return fail(STPDE_EUNSUPPORTED, "the training forward needs at least 3 linear layers");
-    if (!grid || !q || !W || !B || !y || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
-    if (P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
+    const bool empty = P.total_pts == 0;
+    if (!grid || !W || !B || !workspace || !status || (!empty && (!q || !y))) return fail(STPDE_EINVAL, "null pointer argument");
+    if (!empty && P.spec.kc > 1 && !jets) return fail(STPDE_EINVAL, "jets buffer required when derivatives are requested");
     return run_backward(kBwdForwardOnly, P, desc, grid, q, W, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, y, jets,
                         (char*)workspace, workspace_bytes, status, (cudaStream_t)stream);
 }
@@ -558,8 +560,10 @@ int stpde_jet_backward(const stpde_desc_t* desc, const float* grid, const int64_
     int rc = make_plan(P, desc, grid_strides, q_strides);
     if (rc) return rc;
     if (P.n_layers < 3) return fail(STPDE_EUNSUPPORTED, "the fused backward needs at least 3 linear layers");
-    if (!grid || !q || !W || !B || !gy || !gW || !gB || !workspace || !status) return fail(STPDE_EINVAL, "null pointer argument");
-    if (P.spec.kc > 1 && !gjets) return fail(STPDE_EINVAL, "gjets required when derivatives were requested");
+    const bool empty = P.total_pts == 0;
+    if (!grid || !W || !B || !gW || !gB || !workspace || !status || (!empty && (!q || !gy)))
+        return fail(STPDE_EINVAL, "null pointer argument");
+    if (!empty && P.spec.kc > 1 && !gjets) return fail(STPDE_EINVAL, "gjets required when derivatives were requested");
     for (int l = 0; l < P.n_layers; ++l)
         if (!W[l] || !B[l] || !gW[l] || !gB[l]) return fail(STPDE_EINVAL, "null weight / gradient pointer for layer %d", l);
     return run_backward(reuse_forward ? kBwdReuse : kBwdFull, P, desc, grid, q, W, B, gy, gjets, gW, gB, ggrid, gbeta,

@@ -380,5 +380,14 @@ def test_backward_empty_and_tiny_batches(dev):
     ggrid, gW, gB = jets.raw_backward(grid, q0, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3",
                                       torch.empty(1, 0, o, device=dev), torch.empty(spec.n_jet, 1, 0, o, device=dev))
     assert ggrid.abs().max() == 0 and all(g.abs().max() == 0 for g in gW + gB)
+    # the public API with an empty batch: shapes only, through forward, residual programs and backward
+    model = sp.ImNet(dim=3, in_features=c, out_features=o, nf=nf, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    g2 = grid.clone().requires_grad_(True)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, g2, pts, 0., 1.))
+    y, res = layer(q0)
+    assert y.shape == (1, 0, o) and all(v.shape == (1, 0, 1) for v in res.values())
+    (y.sum() + torch.stack(list(res.values())).sum()).backward()
+    assert g2.grad is not None and g2.grad.abs().max() == 0
     errs = run_case(dev, d, (3, 4, 5), c, o, nf, "softplus", *RB2, p=1, precision="fp16x3", seed=14)
     assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
