@@ -680,7 +680,7 @@ int stpde_residuals_backward(int32_t batch, int32_t npts, int32_t dim, int32_t o
     static thread_local ResidualProgramBig rp;
     if (prog_words < 0 || prog_words > 2048 || (prog_words & 1)) return fail(STPDE_EUNSUPPORTED, "adjoint program too long (%d words)", prog_words);
     if (n_consts < 0 || n_consts > 256) return fail(STPDE_EUNSUPPORTED, "too many constants (%d)", n_consts);
-    if (!gres || !gy || (n_jet > 0 && !gjets)) return fail(STPDE_EINVAL, "null pointer argument");
+    if ((int64_t)batch * npts > 0 && (!gres || !gy || (n_jet > 0 && !gjets))) return fail(STPDE_EINVAL, "null pointer argument");
     const int n_out = out_features * (1 + n_jet);
     int sp = 0, out = 0;
     for (int w = 0; w < prog_words; w += 2) {
