@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
 
 // ----------------------------------------------------------------------------------------------
 // vertex_backward (weights): gb_l[n] = sum_v gVb[v][cat],  gW_l[n][kh + dim + ch] = sum_v gVb[v][cat] latent[v][ch]
-// block = 128 cats x one slice of 256 vertices; channel tiles of 32 keep the accumulators in registers
+// block = 128 cats x one slice of kVbSlice vertices; channel tiles of 32 keep the accumulators in registers
 // ----------------------------------------------------------------------------------------------
-constexpr int kVbSlice = 256;
+constexpr int kVbSlice = 32;      // vertices per block: enough blocks to fill the GPU for a 1024-vertex grid
 
 __global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int nvert_total, VertexBwdArgs a) {
     __shared__ float lat[16][33];
@@ -302,8 +302,11 @@ __global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int 
     if (ok) atomicAdd(a.gB[l] + n, bsum);
 }
 
-// vertex_backward (latent grid): ggrid[v][ch] = (1/S) sum_cat gVb[v][cat] * W_l(cat)[n(cat)][kh + dim + ch]
-// block = 8 vertices x 32 channels, cat tiles of 128 staged in shared memory
+// vertex_backward (latent grid): ggrid[v][ch] += (1/S) sum_{cat in slice} gVb[v][cat] * W_l(cat)[n(cat)][kh + dim + ch]
+// block = 8 vertices x 32 channels x one slice of kGridCatSlice cats (blockIdx.z), cat tiles of 128 staged in shared
+// memory; ggrid is zeroed by the caller and the slices are added with atomics
+constexpr int kGridCatSlice = 512;
+
 __global__ void __launch_bounds__(256) vertex_backward_grid_kernel(GridGeom g, int nvert_total, VertexBwdArgs a,
                                                                    float* __restrict__ ggrid) {
     __shared__ float gv[8][128];
@@ -312,17 +315,18 @@ __global__ void __launch_bounds__(256) vertex_backward_grid_kernel(GridGeom g, i
     const int vi = threadIdx.x >> 5;
     const int v = blockIdx.x * 8 + vi;
     const int c = g.channels;
+    const int cat_begin = blockIdx.z * kGridCatSlice, cat_end = min(cat_begin + kGridCatSlice, a.ncat);
     float acc = 0.f;
-    for (int cat0 = 0; cat0 < a.ncat; cat0 += 128) {
+    for (int cat0 = cat_begin; cat0 < cat_end; cat0 += 128) {
         __syncthreads();
         for (int e = threadIdx.x; e < 8 * 128; e += blockDim.x) {
             const int vv = blockIdx.x * 8 + e / 128, cat = cat0 + e % 128;
-            gv[e / 128][e % 128] = (vv < nvert_total && cat < a.ncat) ? a.g_vb[(int64_t)vv * a.ncat + cat] : 0.f;
+            gv[e / 128][e % 128] = (vv < nvert_total && cat < cat_end) ? a.g_vb[(int64_t)vv * a.ncat + cat] : 0.f;
         }
         if (threadIdx.x < 128) {
             const int cat = cat0 + threadIdx.x;
             const float* p = nullptr;
-            if (cat < a.ncat) {
+            if (cat < cat_end) {
                 int l = 0;
                 while (l + 1 < a.n_layers - 1 && cat >= a.cat_off[l + 1]) ++l;
                 p = a.W[l] + (int64_t)(cat - a.cat_off[l]) * a.in_features[l] + a.kh[l] + g.dim;
@@ -331,11 +335,11 @@ __global__ void __launch_bounds__(256) vertex_backward_grid_kernel(GridGeom g, i
         }
         __syncthreads();
         if (ch < c) {
-            const int lim = min(128, a.ncat - cat0);
+            const int lim = min(128, cat_end - cat0);
             for (int t = 0; t < lim; ++t) acc = fmaf(gv[vi][t], __ldg(wrow[t] + ch), acc);
         }
     }
-    if (v < nvert_total && ch < c) ggrid[(int64_t)v * c + ch] = acc * a.scale[1];
+    if (v < nvert_total && ch < c) atomicAdd(ggrid + (int64_t)v * c + ch, acc * a.scale[1]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -406,7 +410,7 @@ void launch_vertex_backward(const GridGeom& g, int nvert_total, const VertexBwdA
     dim3 gw((a.ncat + 127) / 128, (nvert_total + kVbSlice - 1) / kVbSlice);
     vertex_backward_w_kernel<<<gw, 128, 0, st>>>(g, nvert_total, a);
     if (ggrid) {
-        dim3 gg((nvert_total + 7) / 8, (g.channels + 31) / 32);
+        dim3 gg((nvert_total + 7) / 8, (g.channels + 31) / 32, (a.ncat + kGridCatSlice - 1) / kGridCatSlice);
         vertex_backward_grid_kernel<<<gg, 256, 0, st>>>(g, nvert_total, a, ggrid);
     }
 }
