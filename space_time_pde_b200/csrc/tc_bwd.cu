@@ -69,6 +69,8 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
     if (split_weights) cudaMemsetAsync(tc.absmax, 0, 256, st);
     tc.ld0 = round_up(widths[0], 64);
     tc.n0 = widths[0];
+    const char* pair_env = getenv("STPDE_TC_PAIR");
+    tc.use_pair_wide = pair_env ? atoi(pair_env) : 1;
 
     // chunk planes
     char* p = chunk_ws;
@@ -182,7 +184,10 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
         a.z_out = L.z;
         a.ldz = L.ldz;
         ProfScope ps(kSlotGemm + l - 1, st);
-        int rc = tc_launch_pair_save(spec.kc, tc.num_sms, L.w_hi, L.w_lo, L.fa_hi, L.fa_lo, spec, a, st);
+        // features >= 256: CTA-pair tile (M = 256); narrower layers: one 128-feature CTA per SM
+        int rc = L.n_feat >= 2 * tc::kTileF && tc.use_pair_wide
+                     ? tc_launch_pair_save(spec.kc, tc.num_sms, L.w_hi, L.w_lo, L.fa_hi, L.fa_lo, spec, a, st)
+                     : tc_launch_single_save(spec.kc, tc.num_sms, L.w_hi, L.w_lo, L.fa_hi, L.fa_lo, spec, a, st);
         if (rc) return rc;
     }
     return STPDE_OK;
@@ -263,15 +268,18 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         a.g_wx = gW[l - 1] + kh_below;
         a.g_wx_ld = in_features[l - 1];
         ProfScope ps(kSlotDgrad + l - 1, st);
+        const bool wide = L.kh >= 2 * tc::kTileF && tc.use_pair_wide;   // M extent of the dgrad = features of layer l-1
         int rc;
         if (l >= 2) {
             a.z_in = tc.layer[l - 1].z;
             a.ldz = tc.layer[l - 1].ldz;
             a.out_hi = tc.layer[l - 1].zb[0];
             a.out_lo = tc.layer[l - 1].zb[1];
-            rc = tc_launch_pair_bwd(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st);
+            rc = wide ? tc_launch_pair_bwd(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st)
+                      : tc_launch_single_bwd(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st);
         } else {
-            rc = tc_launch_pair_bwd0(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st);
+            rc = wide ? tc_launch_pair_bwd0(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st)
+                      : tc_launch_single_bwd0(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st);
         }
         if (rc) return rc;
     }

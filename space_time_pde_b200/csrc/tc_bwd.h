@@ -29,7 +29,7 @@ struct TcBwdLayer {               // hidden layer l = 1 .. n_layers-2
 };
 
 struct TcBwdContext {
-    int n_layers, kc, rows, passes, num_sms;
+    int n_layers, kc, rows, passes, num_sms, use_pair_wide;
     int ld0, n0;
     TcBwdLayer layer[kMaxLayers];
     float* wscale;
@@ -63,6 +63,14 @@ int tc_launch_pair_bwd(int kc, int num_sms, const CUtensorMap& w_hi, const CUten
                        const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 int tc_launch_pair_bwd0(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
                         const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+
+// single-CTA variants (M = 128) for layers narrower than a CTA-pair tile
+int tc_launch_single_save(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                          const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+int tc_launch_single_bwd(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                         const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
+int tc_launch_single_bwd0(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                          const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 
 // shared with tc_path.cu
 int tc_make_map_2d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1);

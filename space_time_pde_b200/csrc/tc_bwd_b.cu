@@ -11,4 +11,12 @@ int tc_launch_pair_bwd(int kc, int num_sms, const CUtensorMap& w_hi, const CUten
     STPDE_TC_DISPATCH_KC(kc, (rc = launch_layer_pair_mode<KC, tc::kModeBwd>(num_sms, w_hi, w_lo, a_hi, a_lo, spec, a, st)));
     return rc;
 }
+
+int tc_launch_single_bwd(int kc, int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                          const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
+    int rc = STPDE_OK;
+    if (spec_is_rb2(spec)) return launch_layer_mode<6, tc::kModeBwd, tc::kSpecRb2>(num_sms, w_hi, w_lo, a_hi, a_lo, spec, a, st);
+    STPDE_TC_DISPATCH_KC(kc, (rc = launch_layer_mode<KC, tc::kModeBwd>(num_sms, w_hi, w_lo, a_hi, a_lo, spec, a, st)));
+    return rc;
+}
 }  // namespace stpde

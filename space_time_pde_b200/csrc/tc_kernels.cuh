@@ -206,7 +206,255 @@ constexpr int kModeFwdSave = 1;   // forward layer that also stores its pre-acti
 constexpr int kModeBwd = 2;       // dgrad of layer l (W_l^T . zbar_l) + reverse jet activation of layer l-1 >= 1
 constexpr int kModeBwd0 = 3;      // dgrad of layer 1 + reverse of the closed-form layer 0
 
-template <int KC, int SPEC = 0>
+// One tile of the reverse-mode epilogue (shared by the CTA-pair and the single-CTA kernel).
+// The accumulator holds S * 2^sw * abar[c][r][g]: the adjoint of the activations of the layer BELOW the contraction
+// (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with the saved z planes
+// and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the closed-form layer 0 (nothing below it:
+// only the parameter adjoints are accumulated).  Rows are processed in steps of H (4 or 2).
+//   f0        first feature of this CTA's 128-feature slice of the tile, r0 first row of the tile
+//   taddr     TMEM address of the accumulator (lane quarter and buffer already applied)
+//   next_f0   first of this WARP's 32 features in its next tile (or -1), next_r0 that tile's first row (L2 prefetch)
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ>
+__device__ __forceinline__ void bwd_epilogue_tile(const JetSpec& spec, const LayerArgs& args, int f0, int r0, int quarter,
+                                                  int sub, int lane, uint32_t taddr, uint32_t tfull_addr,
+                                                  uint32_t tfull_parity, int next_f0, int next_r0) {
+    constexpr int H = (MODE == kModeBwd0 || KC <= 3) ? 4 : 2;  // rows per step (register budget: 96 per thread)
+    constexpr int PC = (MODE == kModeBwd) ? KC : 1;            // prefetched values per row
+    // MODE 3 prefetches the next step's z0 into registers (dependent vertex gather); MODE 2 relies on the L2
+    // prefetch of the next tile - a register double buffer of K values per row spills inside the hot loop and the
+    // spill store then waits for the load it was meant to hide.
+    constexpr bool kPrefetch = (MODE == kModeBwd0);
+    const bool three = args.passes == 3;
+    const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
+    const int64_t plane = (int64_t)args.rows * args.ld_out;
+    const int64_t zplane = (int64_t)args.rows * args.ldz;
+    const int n_first = spec.n_first;
+    const bool swish_beta_rt = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
+    const int g = f0 + quarter * 32 + lane;
+    const bool g_store = g < args.n_store;
+    const bool g_ok = g < args.n_feat;
+    float bsum = 0.f;                                       // Swish only: d loss / d beta of this thread's elements
+    float G[kMaxDim], A[KC];                                // per-tile partial sums of the coordinate-column adjoint
+#pragma unroll
+    for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) A[c] = 0.f;
+    float wx[kMaxDim], cf[KC];                              // MODE 3: layer-0 coordinate columns / jet coefficients
+#pragma unroll
+    for (int k = 0; k < kMaxDim; ++k)
+        wx[k] = (MODE == kModeBwd0 && k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        float wa = 1.f, wb = 1.f;
+        if constexpr (MODE == kModeBwd0) {
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) {
+                if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
+                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
+                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
+            }
+        }
+        cf[c] = wa * wb;
+    }
+    // operands of one half block: MODE 2 the saved pre-activations, MODE 3 the recomputed z0 of layer 0
+    auto fetch = [&](int row0, float (&pz)[PC][H]) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const int rc = min(row0 + j, args.rows - 1);
+            if constexpr (MODE == kModeBwd) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+                    pz[c][j] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
+            } else {
+                float z0 = g_ok ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + rc) * args.ncat + args.cat_off + g) : 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (k < args.dim) z0 = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + rc), z0);
+                pz[0][j] = z0;
+            }
+        }
+    };
+    float zc[PC][H], zn[PC][H];
+    if (kPrefetch && sub < NRB) fetch(r0 + sub * 8, zc);
+    if constexpr (MODE == kModeBwd) {
+        // The z planes stream from HBM (no reuse): pull the lines of this warp's NEXT tile into L2 now, one
+        // 128-byte line (32 features of one row and component) per lane.
+        if (next_f0 >= 0 && next_f0 < args.n_feat) {
+            for (int rb = sub; rb < NRB; rb += EPI_PQ) {
+                const int r0n = next_r0 + rb * 8;
+                for (int idx = lane; idx < KC * 8; idx += 32) {
+                    const int rn = min(r0n + (idx & 7), args.rows - 1);
+                    prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + next_f0);
+                }
+            }
+        }
+    }
+    mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
+    tc_fence_after();
+    float amax = 0.f;
+#pragma unroll 1
+    for (int rb = sub; rb < NRB; rb += EPI_PQ) {
+#pragma unroll 1
+        for (int h = 0; h < 8 / H; ++h) {                  // rolled: the unrolled epilogue overflowed the i-cache
+            const int rbase = r0 + rb * 8 + h * H;
+            uint32_t v[KC][H];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                if constexpr (H == 4) tmem_ld_x4(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
+                else tmem_ld_x2(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
+            }
+            if constexpr (kPrefetch) {
+                if (h + 1 < 8 / H) fetch(rbase + H, zn);
+                else if (rb + EPI_PQ < NRB) fetch(r0 + (rb + EPI_PQ) * 8, zn);
+            } else {
+                fetch(rbase, zc);
+            }
+            tmem_wait_ld();
+            dispatch_act(args.act, [&](auto act_c) {
+            constexpr int kAct = decltype(act_c)::value;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const int r = rbase + j;
+                const bool r_ok = r < args.rows;
+                const int rc = min(r, args.rows - 1);
+                const int vrow = __ldg(args.vtx + rc);        // L1-resident: shared by every feature of the tile
+                float xr[kMaxDim];
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
+                float ab[KC];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
+                float s1, s2, s3, z0b;
+                act_d123_fast(kAct, args.beta, zc[0][j], s1, s2, s3);
+                if constexpr (MODE == kModeBwd) {
+                    float zb[KC];
+                    float u = 0.f, w3 = 0.f;
+                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) { u = fmaf(ab[c], zc[c][j], u); zb[c] = s1 * ab[c]; }
+                        const float p4 = ab[4] * zc[2][j], p5 = ab[5] * zc[3][j];
+                        w3 = fmaf(p4, zc[2][j], p5 * zc[3][j]);
+                        zb[2] = fmaf(2.f * s2, p4, zb[2]);
+                        zb[3] = fmaf(2.f * s2, p5, zb[3]);
+                    } else {
+                        float cross[STPDE_MAX_FIRST];
+#pragma unroll
+                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) {
+                            u = fmaf(ab[c], zc[c][j], u);
+                            zb[c] = s1 * ab[c];
+                            if (c > n_first) {                 // second order (warp-uniform): parents za, zp
+                                float za = 0.f, zp = 0.f;
+#pragma unroll
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                    if (1 + k < KC) {
+                                        za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
+                                        zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
+                                    }
+                                }
+                                w3 = fmaf(ab[c] * za, zp, w3);
+#pragma unroll
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                    if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                            if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
+                    }
+                    z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
+                    zb[0] = z0b;
+                    if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
+                        float sb0, sb1, sb2;
+                        swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
+                        bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
+                    }
+#pragma unroll
+                    for (int c = 1; c < KC; ++c) A[c] += zb[c];
+                    if (g_store && r_ok) {
+                        const int64_t off = (int64_t)r * args.ld_out + g;
+                        __half* ph = args.out_hi + off;
+                        __half* pl = args.out_lo + off;
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) {
+                            const float xs = zb[c];
+                            amax = fmaxf(amax, fabsf(xs));
+                            const __half hi = __float2half_rn(xs);
+                            *ph = hi;
+                            if (three) *pl = __float2half_rn(xs - __half2float(hi));
+                            ph += plane; pl += plane;
+                        }
+                    }
+                } else {
+                    // layer 0: a_c = sigma^(order_c)(z0) * cf_c
+                    float t1 = 0.f, t2 = 0.f;
+                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                        t1 = fmaf(ab[1], cf[1], fmaf(ab[2], cf[2], ab[3] * cf[3]));
+                        t2 = fmaf(ab[4], cf[4], ab[5] * cf[5]);
+#pragma unroll
+                        for (int c = 1; c < 4; ++c) A[c] = fmaf(ab[c], s1, A[c]);
+                        A[4] = fmaf(ab[4], s2, A[4]);
+                        A[5] = fmaf(ab[5], s2, A[5]);
+                    } else {
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) {
+                            const float pc = ab[c] * cf[c];
+                            if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
+                            else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
+                        }
+                    }
+                    z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
+                    if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
+                        float sb0, sb1, sb2;
+                        swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
+                        bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
+                if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+            }
+            });
+            if constexpr (kPrefetch) {
+#pragma unroll
+                for (int c = 0; c < PC; ++c)
+#pragma unroll
+                    for (int j = 0; j < H; ++j) zc[c][j] = zn[c][j];
+            }
+        }
+    }
+    if (g_ok) {
+        // fold the per-component sums into the coordinate columns (once per tile)
+#pragma unroll
+        for (int c = 1; c < KC; ++c) {
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) {
+                if (spec.kind[c] == 1 && k == spec.dir[c]) G[k] += A[c];
+                if constexpr (MODE == kModeBwd0) {
+                    if (spec.kind[c] == 2) {
+                        const int da = spec.dir[spec.pa[c]], db = spec.dir[spec.pb[c]];
+                        float wda = 0.f, wdb = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < kMaxDim; ++kk) { if (kk == da) wda = wx[kk]; if (kk == db) wdb = wx[kk]; }
+                        if (k == da) G[k] = fmaf(A[c], wdb, G[k]);
+                        if (k == db) G[k] = fmaf(A[c], wda, G[k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k)
+            if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
+    }
+    if (swish_beta_rt) {
+        for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+        if (lane == 0) atomicAdd(args.g_beta, bsum);
+    }
+    if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+}
+
+template <int KC, int SPEC = 0, int MODE = kModeFwd>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -311,6 +559,23 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
+    } else if (MODE >= kModeBwd) {
+        // ===================== reverse-mode epilogue (bwd_epilogue_tile) =====================
+        const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
+            const int tn = t + gridDim.x;
+            const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF + quarter * 32 : -1;
+            const int next_r0 = (tn / n_ftiles) * NR;
+            bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane,
+                                                                   tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N,
+                                                                   smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[buf]));
+        }
     } else {
         // ===================== epilogue warps: TMEM -> jets activation -> global =====================
         // Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter alternate 8-row blocks.
@@ -374,6 +639,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
                     float s0, s1, s2;
                     act_jet_fast(kAct, args.beta, zt[0] + zs[i], s0, s1, s2);
+                    if constexpr (MODE == kModeFwdSave) {
+                        if (g < args.n_feat && r < args.rows) {     // pre-activations for the reverse sweep
+                            const int64_t zplane = (int64_t)args.rows * args.ldz;
+                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
+                            *pz = zt[0] + zs[i];
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
+                        }
+                    }
                     o[0] = s0 * fmask;
                     s1 *= fmask;
                     s2 *= fmask;
@@ -727,258 +1001,21 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             }
         }
     } else if (MODE >= kModeBwd && warp < 2 + kEpiW) {
-        // ===================== reverse-mode epilogue =====================
-        // The accumulator holds S * 2^sw * abar[c][r][g]: the adjoint of the activations of the layer BELOW the
-        // contraction (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with
-        // the saved z planes and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the
-        // closed-form layer 0 (nothing below it: only the parameter adjoints are accumulated).
-        // Rows are processed in steps of H (4 or 2): the z operands of the next half block are in flight while the
-        // current one is evaluated (the dependent vertex gather of MODE 3 would otherwise serialise every row).
-        constexpr int H = (MODE == kModeBwd0 || KC <= 3) ? 4 : 2;  // rows per step (register budget: 96 per thread)
-        constexpr int PC = (MODE == kModeBwd) ? KC : 1;            // prefetched values per row
-        // MODE 3 prefetches the next step's z0 into registers (dependent vertex gather); MODE 2 relies on the L2
-        // prefetch of the next tile below - a register double buffer of K values per row spills inside the hot loop
-        // and the spill store then waits for the load it was meant to hide.
-        constexpr bool kPrefetch = (MODE == kModeBwd0);
+        // ===================== reverse-mode epilogue (bwd_epilogue_tile) =====================
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
-        const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
-        const int64_t plane = (int64_t)args.rows * args.ld_out;
-        const int64_t zplane = (int64_t)args.rows * args.ldz;
-        const int n_first = spec.n_first;
-        const bool swish_beta_rt = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
         for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
             const int buf = it & 1;
             const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
-            const int g = f0 + quarter * 32 + lane;
-            const bool g_store = g < args.n_store;
-            const bool g_ok = g < args.n_feat;
-            float bsum = 0.f;                                       // Swish only: d loss / d beta of this thread's elements
-            float G[kMaxDim], A[KC];                                // per-tile partial sums of the coordinate-column adjoint
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
-#pragma unroll
-            for (int c = 0; c < KC; ++c) A[c] = 0.f;
-            float wx[kMaxDim], cf[KC];                              // MODE 3: layer-0 coordinate columns / jet coefficients
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k)
-                wx[k] = (MODE == kModeBwd0 && k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                float wa = 1.f, wb = 1.f;
-                if constexpr (MODE == kModeBwd0) {
-#pragma unroll
-                    for (int k = 0; k < kMaxDim; ++k) {
-                        if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
-                        if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
-                        if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
-                    }
-                }
-                cf[c] = wa * wb;
-            }
-            // operands of one half block: MODE 2 the saved pre-activations, MODE 3 the recomputed z0 of layer 0
-            auto fetch = [&](int row0, float (&pz)[PC][H]) {
-#pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const int rc = min(row0 + j, args.rows - 1);
-                    if constexpr (MODE == kModeBwd) {
-#pragma unroll
-                        for (int c = 0; c < KC; ++c)
-                            pz[c][j] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
-                    } else {
-                        float z0 = g_ok ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + rc) * args.ncat + args.cat_off + g) : 0.f;
-#pragma unroll
-                        for (int k = 0; k < kMaxDim; ++k)
-                            if (k < args.dim) z0 = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + rc), z0);
-                        pz[0][j] = z0;
-                    }
-                }
-            };
-            float zc[PC][H], zn[PC][H];
-            if (kPrefetch && sub < NRB) fetch(r0 + sub * 8, zc);
-            if constexpr (MODE == kModeBwd) {
-                // The z planes stream from HBM (no reuse): pull the lines of this warp's NEXT tile into L2 now, one
-                // 128-byte line (32 features of one row and component) per lane, so that the register prefetch above
-                // sees an L2 hit instead of the full DRAM latency once per step.
-                const int tn = t + n_pairs;
-                const int f0n = (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32;
-                if (tn < n_tiles && f0n < args.n_feat) {
-                    for (int rb = sub; rb < NRB; rb += kEpiPQ) {
-                        const int r0n = (tn / n_ftiles) * NR + rb * 8;
-                        for (int idx = lane; idx < KC * 8; idx += 32) {
-                            const int rn = min(r0n + (idx & 7), args.rows - 1);
-                            prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + f0n);
-                        }
-                    }
-                }
-            }
-            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status, args.wait_ns);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            float amax = 0.f;
-#pragma unroll 1
-            for (int rb = sub; rb < NRB; rb += kEpiPQ) {
-#pragma unroll 1
-                for (int h = 0; h < 8 / H; ++h) {                  // rolled: the unrolled epilogue overflowed the i-cache
-                    const int rbase = r0 + rb * 8 + h * H;
-                    uint32_t v[KC][H];
-#pragma unroll
-                    for (int c = 0; c < KC; ++c) {
-                        if constexpr (H == 4) tmem_ld_x4(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
-                        else tmem_ld_x2(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
-                    }
-                    if constexpr (kPrefetch) {
-                        if (h + 1 < 8 / H) fetch(rbase + H, zn);
-                        else if (rb + kEpiPQ < NRB) fetch(r0 + (rb + kEpiPQ) * 8, zn);
-                    } else {
-                        fetch(rbase, zc);
-                    }
-                    tmem_wait_ld();
-                    dispatch_act(args.act, [&](auto act_c) {
-                    constexpr int kAct = decltype(act_c)::value;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        const int r = rbase + j;
-                        const bool r_ok = r < args.rows;
-                        const int rc = min(r, args.rows - 1);
-                        const int vrow = __ldg(args.vtx + rc);        // L1-resident: shared by every feature of the tile
-                        float xr[kMaxDim];
-#pragma unroll
-                        for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
-                        float ab[KC];
-#pragma unroll
-                        for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
-                        float s1, s2, s3, z0b;
-                        act_d123_fast(kAct, args.beta, zc[0][j], s1, s2, s3);
-                        if constexpr (MODE == kModeBwd) {
-                            float zb[KC];
-                            float u = 0.f, w3 = 0.f;
-                            if constexpr (SPEC == kSpecRb2 && KC == 6) {
-#pragma unroll
-                                for (int c = 1; c < KC; ++c) { u = fmaf(ab[c], zc[c][j], u); zb[c] = s1 * ab[c]; }
-                                const float p4 = ab[4] * zc[2][j], p5 = ab[5] * zc[3][j];
-                                w3 = fmaf(p4, zc[2][j], p5 * zc[3][j]);
-                                zb[2] = fmaf(2.f * s2, p4, zb[2]);
-                                zb[3] = fmaf(2.f * s2, p5, zb[3]);
-                            } else {
-                                float cross[STPDE_MAX_FIRST];
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
-#pragma unroll
-                                for (int c = 1; c < KC; ++c) {
-                                    u = fmaf(ab[c], zc[c][j], u);
-                                    zb[c] = s1 * ab[c];
-                                    if (c > n_first) {                 // second order (warp-uniform): parents za, zp
-                                        float za = 0.f, zp = 0.f;
-#pragma unroll
-                                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                            if (1 + k < KC) {
-                                                za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
-                                                zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
-                                            }
-                                        }
-                                        w3 = fmaf(ab[c] * za, zp, w3);
-#pragma unroll
-                                        for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                                            if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
-                                    }
-                                }
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                                    if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
-                            }
-                            z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
-                            zb[0] = z0b;
-                            if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
-                                float sb0, sb1, sb2;
-                                swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
-                                bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
-                            }
-#pragma unroll
-                            for (int c = 1; c < KC; ++c) A[c] += zb[c];
-                            if (g_store && r_ok) {
-                                const int64_t off = (int64_t)r * args.ld_out + g;
-                                __half* ph = args.out_hi + off;
-                                __half* pl = args.out_lo + off;
-#pragma unroll
-                                for (int c = 0; c < KC; ++c) {
-                                    const float xs = zb[c];
-                                    amax = fmaxf(amax, fabsf(xs));
-                                    const __half hi = __float2half_rn(xs);
-                                    *ph = hi;
-                                    if (three) *pl = __float2half_rn(xs - __half2float(hi));
-                                    ph += plane; pl += plane;
-                                }
-                            }
-                        } else {
-                            // layer 0: a_c = sigma^(order_c)(z0) * cf_c
-                            float t1 = 0.f, t2 = 0.f;
-                            if constexpr (SPEC == kSpecRb2 && KC == 6) {
-                                t1 = fmaf(ab[1], cf[1], fmaf(ab[2], cf[2], ab[3] * cf[3]));
-                                t2 = fmaf(ab[4], cf[4], ab[5] * cf[5]);
-#pragma unroll
-                                for (int c = 1; c < 4; ++c) A[c] = fmaf(ab[c], s1, A[c]);
-                                A[4] = fmaf(ab[4], s2, A[4]);
-                                A[5] = fmaf(ab[5], s2, A[5]);
-                            } else {
-#pragma unroll
-                                for (int c = 1; c < KC; ++c) {
-                                    const float pc = ab[c] * cf[c];
-                                    if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
-                                    else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
-                                }
-                            }
-                            z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
-                            if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
-                                float sb0, sb1, sb2;
-                                swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
-                                bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
-                        if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
-                    }
-                    });
-                    if constexpr (kPrefetch) {
-#pragma unroll
-                        for (int c = 0; c < PC; ++c)
-#pragma unroll
-                            for (int j = 0; j < H; ++j) zc[c][j] = zn[c][j];
-                    }
-                }
-            }
-            if (g_ok) {
-                // fold the per-component sums into the coordinate columns (once per tile)
-#pragma unroll
-                for (int c = 1; c < KC; ++c) {
-#pragma unroll
-                    for (int k = 0; k < kMaxDim; ++k) {
-                        if (spec.kind[c] == 1 && k == spec.dir[c]) G[k] += A[c];
-                        if constexpr (MODE == kModeBwd0) {
-                            if (spec.kind[c] == 2) {
-                                const int da = spec.dir[spec.pa[c]], db = spec.dir[spec.pb[c]];
-                                float wda = 0.f, wdb = 0.f;
-#pragma unroll
-                                for (int kk = 0; kk < kMaxDim; ++kk) { if (kk == da) wda = wx[kk]; if (kk == db) wdb = wx[kk]; }
-                                if (k == da) G[k] = fmaf(A[c], wdb, G[k]);
-                                if (k == db) G[k] = fmaf(A[c], wda, G[k]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
-            }
-            if (swish_beta_rt) {
-                for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
-                if (lane == 0) atomicAdd(args.g_beta, bsum);
-            }
-            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+            const int tn = t + n_pairs;
+            const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32 : -1;
+            const int next_r0 = (tn / n_ftiles) * NR;
+            bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPQ>(spec, args, f0, r0, quarter, sub, lane,
+                                                           tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N,
+                                                           smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);

@@ -94,6 +94,28 @@ static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CU
     return STPDE_OK;
 }
 
+// Single-CTA kernel (M = 128 features per CTA, one CTA per SM) in a training mode: used for the narrow layers, where
+// a 256-feature CTA-pair tile would leave one CTA (and most epilogue warps) idle.
+template <int KC, int MODE, int SPEC = 0>
+static int launch_layer_mode(int num_sms, const CUtensorMap& w_hi, const CUtensorMap& w_lo, const CUtensorMap& a_hi,
+                             const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
+    constexpr int NR = tc::rows_per_tile(KC);
+    constexpr int N = KC * NR;
+    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
+    static unsigned long long configured = 0;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!(configured >> (dev_ & 63) & 1ull)) {
+        if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel, training mode) failed");
+        configured |= 1ull << (dev_ & 63);
+    }
+    const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    tc::tc_layer_kernel<KC, SPEC, MODE><<<grid, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    return STPDE_OK;
+}
+
 #endif  // STPDE_TC_LAUNCH_IMPL
 
 }  // namespace stpde
