@@ -15,7 +15,9 @@ npts = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 jets.set_default_precision(precision)
 dev = torch.device("cuda:0")
-model = bench.make_model(dev)
+nf = int(os.environ.get("NF", bench.NF))
+torch.manual_seed(0)
+model = sp.ImNet(dim=3, in_features=bench.CHANNELS, out_features=4, nf=nf, activation=sp.NONLINEARITIES[bench.ACT]).to(dev)
 grid, q = bench.synthetic_inputs(1234, dev, npts)
 grid.requires_grad_(True)
 layer = sp.get_rb2_pde_layer(**bench.RB2)

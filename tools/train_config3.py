@@ -58,7 +58,14 @@ def time_it(fn, n):
 
 fwd_ms = time_it(forward_only, 3)
 trn_ms = time_it(train_step, 2)
+from space_time_pde_b200 import _lib
+lib = _lib.load()
+lib.stpde_profile_enable(1)
+_lib.profile_read()
+train_step()
+prof = {k: round(v[0], 1) for k, v in _lib.profile_read().items() if v[1] > 0}
+lib.stpde_profile_enable(0)
 print(json.dumps({"config": "BASELINE config 3 share of one GPU: 8 crops x 131072 points, ImNet nf=32, normalised RB2, "
                             f"precision {precision}, chunks of 8 x {chunk} points",
                   "forward_residuals_ms": fwd_ms, "forward_points_per_s": B * P / (fwd_ms * 1e-3),
-                  "train_step_ms": trn_ms, "train_points_per_s": B * P / (trn_ms * 1e-3)}))
+                  "train_step_ms": trn_ms, "train_points_per_s": B * P / (trn_ms * 1e-3), "train_kernel_ms": prof}))
