@@ -92,15 +92,18 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
     const int O = a.O, Kp = a.Kp, F = a.n_feat, ldo = a.ld_out, dim = a.dim;
     float* Ws = sm;                          // [O][Kp]
     float* ob = Ws + O * Kp;                 // [KC][128][O]
-    float* gWl = ob + KC * 128 * O;          // [O][ldo]
-    float* gWx = gWl + O * ldo;              // [ldo][dim]
-    float* gB = gWx + ldo * dim;             // [O]
+    // partial sums of the last layer's weight adjoint [O][ldo] and of the coordinate-column adjoint [ldo][dim]: one
+    // private copy per warp when shared memory allows (plain read-modify-write, a lane owns its features), else one
+    // shared copy updated with atomics
+    const int copies = a.acc_copies, acc_stride = O * ldo + ldo * dim;
+    float* gWl = ob + KC * 128 * O;
+    float* gB = gWl + copies * acc_stride;   // [O]
     const int ncorner = 1 << dim;
     const int row0 = blockIdx.x * 128;
     const float S = a.scale[0];
     for (int e = threadIdx.x; e < O * Kp; e += blockDim.x) Ws[e] = a.Wlast[e];
     for (int e = threadIdx.x; e < KC * 128 * O; e += blockDim.x) ob[e] = 0.f;
-    for (int e = threadIdx.x; e < O * ldo + ldo * dim + O; e += blockDim.x) gWl[e] = 0.f;
+    for (int e = threadIdx.x; e < copies * acc_stride + O; e += blockDim.x) gWl[e] = 0.f;
     __syncthreads();
 
     // ---- phase 1: one thread per (local row, output); it owns ob[.][lr][o] ----
@@ -157,8 +160,11 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
     const int64_t zplane = (int64_t)a.rows * a.ldz, aplane = (int64_t)a.rows * Kp, oplane = (int64_t)a.rows * ldo;
     const bool swish_beta = a.act == STPDE_ACT_SWISH && a.g_beta != nullptr;
     float amax = 0.f, bsum = 0.f;
-    for (int e = threadIdx.x; e < 128 * ldo; e += blockDim.x) {
-        const int f = e % ldo, lr = e / ldo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* myWl = gWl + (copies > 1 ? warp : 0) * acc_stride;
+    float* myWx = myWl + O * ldo;
+    for (int lr = warp; lr < 128; lr += 8)
+    for (int f = lane; f < ldo; f += 32) {
         const int r = row0 + lr;
         if (r >= a.rows) continue;
         float zb[KC];
@@ -176,7 +182,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
                 float s = 0.f;
 #pragma unroll
                 for (int c = 0; c < KC; ++c) s = fmaf(ob[(c * 128 + lr) * O + o], av[c], s);
-                atomicAdd(gWl + o * ldo + f, s);
+                if (copies > 1) myWl[o * ldo + f] += s;
+                else atomicAdd(myWl + o * ldo + f, s);
             }
             float s1, s2, s3;
             act_d123_fast(a.act, a.beta, z[0], s1, s2, s3);
@@ -206,7 +213,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
 #pragma unroll
                 for (int c = 1; c < KC; ++c)
                     if (spec.kind[c] == 1 && spec.dir[c] == k) s += zb[c];
-                atomicAdd(gWx + f * dim + k, s);
+                if (copies > 1) myWx[f * dim + k] += s;
+                else atomicAdd(myWx + f * dim + k, s);
             }
         } else {
 #pragma unroll
@@ -235,10 +243,15 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
     // ---- flush the CTA's partial sums ----
     for (int e = threadIdx.x; e < O * ldo; e += blockDim.x) {
         const int o = e / ldo, f = e % ldo;
-        if (f < F) atomicAdd(a.g_wlast + (int64_t)o * F + f, gWl[e]);
+        float v = 0.f;
+        for (int cp = 0; cp < copies; ++cp) v += gWl[cp * acc_stride + e];
+        if (f < F) atomicAdd(a.g_wlast + (int64_t)o * F + f, v);
     }
-    for (int e = threadIdx.x; e < F * dim; e += blockDim.x)
-        atomicAdd(a.g_wx + (int64_t)(e / dim) * a.g_wx_ld + e % dim, gWx[e]);
+    for (int e = threadIdx.x; e < F * dim; e += blockDim.x) {
+        float v = 0.f;
+        for (int cp = 0; cp < copies; ++cp) v += gWl[cp * acc_stride + O * ldo + e];
+        atomicAdd(a.g_wx + (int64_t)(e / dim) * a.g_wx_ld + e % dim, v);
+    }
     for (int e = threadIdx.x; e < O; e += blockDim.x) atomicAdd(a.g_blast + e, gB[e]);
 }
 
@@ -370,13 +383,15 @@ void launch_split_weights_t(const float* W, int N, int in_features, int kh, int 
     split_weights_t_kernel<<<148 * 4, 256, 0, st>>>(W, N, in_features, kh, fp, ldz, absmax, hi, lo);
 }
 
-size_t blend_backward_smem(int kc, int O, int Kp, int ldo, int dim) {
-    return (size_t)(O * Kp + kc * 128 * O + O * ldo + ldo * dim + O) * sizeof(float);
+size_t blend_backward_smem(int kc, int O, int Kp, int ldo, int dim, int copies) {
+    return (size_t)(O * Kp + kc * 128 * O + copies * (O * ldo + ldo * dim) + O) * sizeof(float);
 }
 
 template <int KC>
-static int launch_blend_backward_t(const JetSpec& spec, const BlendBwdArgs& a, cudaStream_t st) {
-    const size_t smem = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim);
+static int launch_blend_backward_t(const JetSpec& spec, const BlendBwdArgs& a_in, cudaStream_t st) {
+    BlendBwdArgs a = a_in;
+    a.acc_copies = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim, 8) <= 96 * 1024 ? 8 : 1;   // 2 CTAs / SM stay resident
+    const size_t smem = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim, a.acc_copies);
     if (smem > 200 * 1024) return STPDE_EUNSUPPORTED;
     static unsigned long long configured = 0;
     int dev_ = 0;
