@@ -331,3 +331,29 @@ def test_adjoint_programs_match_autograd_of_the_equations(kind):
         for i in range(o):
             ref = gj[pl][..., i].numpy() if gj is not None else 0.
             assert np.allclose(adj[o + pl * o + i], ref, rtol=1e-9, atol=1e-9)
+
+
+def test_backward_precision_option_and_route_selection():
+    from space_time_pde_b200.equations import JetSpec
+    with pytest.raises(ValueError):
+        jets.set_backward_precision("bf16")
+    jets.set_backward_precision("fp16")
+    assert jets.BACKWARD_PRECISION == "fp16"
+    jets.set_backward_precision("same")
+    q_cpu = torch.zeros(1, 4, 3)
+    spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
+    # the fused reverse sweep needs CUDA points, >= 3 linear layers and no gradient w.r.t. the query points
+    assert not jets.fused_backward_supported(q_cpu, spec, 6, False, False)
+    os.environ["STPDE_BACKWARD"] = "torch"
+    try:
+        assert not jets.fused_backward_supported(q_cpu, spec, 6, False, False)
+    finally:
+        os.environ.pop("STPDE_BACKWARD")
+
+
+def test_non_polynomial_equations_keep_the_torch_route():
+    """sin() cannot be expressed as a postfix program: no residual program, no adjoint program, lambdified torch arithmetic."""
+    layer = sp.PDELayer(in_vars="x, t", out_vars="u")
+    layer.add_equation("dif(u, t) + sin(u) * dif(u, x)", "burgers_like")
+    spec, program = layer._binding()
+    assert spec is not None and program is None and layer._adjoint is None
