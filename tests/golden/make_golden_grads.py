@@ -27,6 +27,7 @@ CASES = {
     "rb2_tanh": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_tanh"]),
     "rb2_softplus": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_softplus"]),
     "rb2_elu": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_elu"]),
+    "rb2_swish": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_swish"]),        # learnable beta: g_beta is stored too
     "rb2_paper_softplus": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_paper_softplus"]),
     "rb2_nonunit_tanh": lambda: mg.get_rb2_pde_layer(**RB2_CASES["rb2_nonunit_tanh"]),
     "generic_d1_softplus": mg.generic_layer(1, 2),
@@ -47,6 +48,8 @@ def main():
             for i in range(6):
                 getattr(model, f"fc{i}").weight.copy_(torch.tensor(z[f"W{i}"], dtype=torch.float64))
                 getattr(model, f"fc{i}").bias.copy_(torch.tensor(z[f"b{i}"], dtype=torch.float64))
+            if act == "swish":
+                model.activ.beta.fill_(float(z["act_param"]))
         xmax = z["xmax"]
         if xmax.ndim == 0:
             xmin_t, xmax_t = 0.0, float(xmax)
@@ -61,6 +64,8 @@ def main():
         for i in range(6):
             arrays[f"g_W{i}"] = getattr(model, f"fc{i}").weight.grad.numpy()
             arrays[f"g_b{i}"] = getattr(model, f"fc{i}").bias.grad.numpy()
+        if act == "swish":
+            arrays["g_beta"] = model.activ.beta.grad.numpy().reshape(1)
         mg.save("grads_" + name, **arrays)
 
 

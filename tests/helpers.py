@@ -73,7 +73,7 @@ def rel_err_quantile(a, b, q=0.995):
     return float(np.quantile(np.abs(a - b) / (den if den > 0 else 1.0), q))
 
 
-GRAD_CASES = ["rb2_tanh", "rb2_softplus", "rb2_elu", "rb2_paper_softplus", "rb2_nonunit_tanh",
+GRAD_CASES = ["rb2_tanh", "rb2_softplus", "rb2_elu", "rb2_swish", "rb2_paper_softplus", "rb2_nonunit_tanh",
               "generic_d1_softplus", "generic_d2_softplus", "generic_d4_softplus"]
 
 

@@ -259,6 +259,8 @@ def test_loss_backward_matches_reference_golden_gradients(name, dev):
     for i in range(6):
         errs[f"W{i}"] = rel_linf(model.fc[i].weight.grad.cpu().numpy(), g[f"g_W{i}"])
         errs[f"b{i}"] = rel_linf(model.fc[i].bias.grad.cpu().numpy(), g[f"g_b{i}"])
+    if "g_beta" in g:   # learnable Swish beta (reference src/nonlinearities.py:5-13): gradient from the same fused sweep
+        errs["beta"] = rel_linf(model.activ.beta.grad.cpu().numpy().reshape(1), g["g_beta"])
     print(name, " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
     assert max(errs.values()) < 1e-4, errs
 

@@ -261,6 +261,8 @@ def test_torch_jet_checker_gradients_match_reference_golden(name, cpu_backend):
     for i in range(6):
         assert rel_linf(model.fc[i].weight.grad.numpy(), g[f"g_W{i}"]) < 2e-4, i
         assert rel_linf(model.fc[i].bias.grad.numpy(), g[f"g_b{i}"]) < 2e-4, i
+    if "g_beta" in g:   # learnable Swish beta (reference src/nonlinearities.py:5-13)
+        assert rel_linf(model.activ.beta.grad.numpy().reshape(1), g["g_beta"]) < 2e-4
 
 
 def _run_postfix(words, consts, q, y, jets, gres=None):
