@@ -39,6 +39,25 @@ class ImNet(nn.Module):
         return self.fc[-1](h)
 
 
+def ddp_wrapper(model: nn.Module):
+    """The ``DistributedDataParallel`` wrapper around ``model`` (reference train_ddp.py: ``imnet = DDP(imnet)``), or None.
+
+    The fused path reads the inner module's parameters directly, so ``DDP.forward`` never runs and DDP's reducer is
+    never armed for that step: the fused backward therefore averages the decoder gradients over the wrapper's
+    process group itself (``jets.FusedJetQuery.backward``), which is what DDP would have done."""
+    from torch.nn.parallel import DistributedDataParallel
+
+    inner = model
+    while isinstance(inner, nn.Module):
+        if isinstance(inner, DistributedDataParallel):
+            return inner
+        nxt = getattr(inner, "module", None)
+        if not isinstance(nxt, nn.Module):
+            return None
+        inner = nxt
+    return None
+
+
 def decoder_signature(model: nn.Module):
     """Return (layers, act_name, act_param) if ``model`` has ImNet's skip-MLP structure, else None.
 

@@ -254,8 +254,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
                  Ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act: str, act_param: float,
                  spec: JetSpec, precision: str, gy: torch.Tensor, gjets: Optional[torch.Tensor],
                  need_grid: bool = True, check: bool = True, stash_token: int = 0):
-    """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l]); the gradient of the
-    Swish beta is left in ``raw_backward.last_gbeta`` (a 1-element tensor, zero for other activations).
+    """Fused reverse sweep (``stpde_jet_backward``): returns (grid_grad | None, [dW_l], [db_l], gbeta); ``gbeta`` is the
+    gradient of the Swish beta (a 1-element tensor, zero for other activations).
 
     ``stash_token``: token of the training forward whose planes may still sit in the device's stash workspace; if it
     is still current the forward is not recomputed.
@@ -277,7 +277,6 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
     ggrid = torch.empty(grid.shape, dtype=torch.float32, device=device) if need_grid else None
     status = torch.zeros(1, dtype=torch.int32, device=device)
     gbeta = torch.zeros(1, dtype=torch.float32, device=device)
-    raw_backward.last_gbeta = gbeta
     wptr = (ctypes.c_void_p * len(Wc))(*[w.data_ptr() for w in Wc])
     bptr = (ctypes.c_void_p * len(Bc))(*[v.data_ptr() for v in Bc])
     gwptr = (ctypes.c_void_p * len(gW))(*[w.data_ptr() for w in gW])
@@ -309,7 +308,7 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
         else:
             raise _lib.StpdeError(-6, "an adjoint left the fp16 range of the split-precision tensor-core backward; "
                                       "set STPDE_BACKWARD=torch to use the autograd re-evaluation")
-    return ggrid, gW, gB
+    return ggrid, gW, gB, gbeta
 
 
 def fused_backward_supported(q: torch.Tensor, spec: JetSpec, n_layers: int, needs_q: bool, needs_beta: bool) -> bool:
@@ -318,6 +317,28 @@ def fused_backward_supported(q: torch.Tensor, spec: JetSpec, n_layers: int, need
         return False
     return (q.is_cuda and n_layers >= 3 and not needs_q
             and 1 + len(spec.first) + len(spec.second) <= _lib.MAX_COMPONENTS)
+
+
+def _ddp_average(ddp, grads) -> None:
+    """Average decoder-parameter gradients over the process group of a DistributedDataParallel wrapper, in place, with
+    ONE all-reduce of a flat buffer (what DDP's reducer does when ``DDP.forward`` runs; the fused path bypasses it).
+    ``ddp.no_sync()`` is honoured (gradient accumulation)."""
+    if ddp is None or not grads or not getattr(ddp, "require_backward_grad_sync", True):
+        return
+    import torch.distributed as dist
+
+    group = getattr(ddp, "process_group", None)
+    world = dist.get_world_size(group)
+    if world <= 1:
+        return
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].reshape(g.shape))
+        off += n
 
 
 class FusedJetQuery(torch.autograd.Function):
@@ -329,6 +350,9 @@ class FusedJetQuery(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, grid, q, lo, hi, act, act_param_t, spec, precision, n_layers, *params):
+        ctx.ddp = None
+        if isinstance(n_layers, tuple):          # (n_layers, DistributedDataParallel wrapper of the decoder)
+            n_layers, ctx.ddp = n_layers
         Ws, bs = params[:n_layers], params[n_layers:]
         beta = float(act_param_t.detach()) if act_param_t is not None else 1.0
         needs = ctx.needs_input_grad
@@ -362,12 +386,13 @@ class FusedJetQuery(torch.autograd.Function):
             if spec.n_jet > 0 and gj is None:
                 gj = torch.zeros(spec.n_jet, *gy.shape, dtype=gy.dtype, device=gy.device)
             bprec = ctx.precision if BACKWARD_PRECISION == "same" else BACKWARD_PRECISION
-            ggrid, gW, gB = raw_backward(grid, q, lo, hi, params[:n_layers], params[n_layers:], act, beta, spec,
-                                         bprec, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
+            ggrid, gW, gB, gbeta = raw_backward(grid, q, lo, hi, params[:n_layers], params[n_layers:], act, beta, spec,
+                                                bprec, gy, gj, need_grid=needs[0], stash_token=ctx.stash_token)
+            _ddp_average(ctx.ddp, list(gW) + list(gB) + [gbeta])
             if needs[0]:
                 result[0] = ggrid
             if has_beta and needs[5]:
-                result[5] = raw_backward.last_gbeta.reshape(beta_t.shape).to(beta_t.dtype)
+                result[5] = gbeta.reshape(beta_t.shape).to(beta_t.dtype)
             for i, g in enumerate(list(gW) + list(gB)):
                 if needs[9 + i]:
                     result[9 + i] = g.to(params[i].dtype)
@@ -405,6 +430,7 @@ class FusedJetQuery(torch.autograd.Function):
                     q_grad[:, sl] = g
                 else:
                     acc[slot] = g if slot not in acc else acc[slot] + g
+        _ddp_average(ctx.ddp, [g for slot, g in acc.items() if slot >= 5])
         for slot, g in acc.items():
             result[slot] = g
         if needs[1]:
@@ -413,12 +439,16 @@ class FusedJetQuery(torch.autograd.Function):
 
 
 def fused_query(grid: torch.Tensor, q: torch.Tensor, xmin, xmax, layers, act: str, act_param,
-                spec: Optional[JetSpec] = None, precision: Optional[str] = None):
-    """y [b,p,o] (and jets [n_jet,b,p,o] when ``spec`` asks for derivatives)."""
+                spec: Optional[JetSpec] = None, precision: Optional[str] = None, ddp=None):
+    """y [b,p,o] (and jets [n_jet,b,p,o] when ``spec`` asks for derivatives).
+
+    ``ddp``: the DistributedDataParallel wrapper the decoder layers came from, if any (its process group receives the
+    gradient averaging the bypassed ``DDP.forward`` would have armed)."""
     spec = spec or JetSpec()
     precision = precision or DEFAULT_PRECISION
     lo, hi = bounds_tensors(xmin, xmax, q.shape[-1], q.device)
     Ws = [l.weight for l in layers]
     bs = [l.bias for l in layers]
-    y, jets = FusedJetQuery.apply(grid, q, lo, hi, act, act_param, spec, precision, len(layers), *Ws, *bs)
+    nl = len(layers) if ddp is None else (len(layers), ddp)
+    y, jets = FusedJetQuery.apply(grid, q, lo, hi, act, act_param, spec, precision, nl, *Ws, *bs)
     return y, (jets if spec.n_jet else None)

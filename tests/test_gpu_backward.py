@@ -71,9 +71,9 @@ def run_case(dev, d, gshape, c, o, nf, act, first, second, p, precision, seed=0,
     gy = (torch.randn(1, p, o, generator=gen) * gscale).to(dev)
     gj = (torch.randn(max(spec.n_jet, 1), 1, p, o, generator=gen) * gscale * 0.05).to(dev) if spec.n_jet else None
     lo, hi = jets.bounds_tensors(0., 1., d, dev)
-    ggrid, gW, gB = jets.raw_backward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, gy, gj)
+    ggrid, gW, gB, gbeta_t = jets.raw_backward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, gy, gj)
     torch.cuda.synchronize()
-    gbeta = float(jets.raw_backward.last_gbeta)
+    gbeta = float(gbeta_t)
     rgrid, rW, rB = reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj)
     errs = {"grid": rel_linf(ggrid.cpu().numpy(), rgrid.cpu().numpy())}
     if act == "swish":
@@ -379,7 +379,7 @@ def test_backward_empty_and_tiny_batches(dev):
     spec = JetSpec(*RB2)
     lo, hi = jets.bounds_tensors(0., 1., d, dev)
     q0 = torch.empty(1, 0, d, device=dev)
-    ggrid, gW, gB = jets.raw_backward(grid, q0, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3",
+    ggrid, gW, gB, _ = jets.raw_backward(grid, q0, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3",
                                       torch.empty(1, 0, o, device=dev), torch.empty(spec.n_jet, 1, 0, o, device=dev))
     assert ggrid.abs().max() == 0 and all(g.abs().max() == 0 for g in gW + gB)
     # the public API with an empty batch: shapes only, through forward, residual programs and backward

@@ -110,7 +110,7 @@ def test_config5_sweep_shape_forward_and_backward(dev):
     gj = (torch.randn(spec.n_jet, 1, n, 4, generator=gen) * 1e-3).to(dev)
     lo, hi = jets.bounds_tensors(0., 1., 3, dev)
     Ws, bs = [l.weight.detach() for l in model.fc], [l.bias.detach() for l in model.fc]
-    ggrid, gW, gB = jets.raw_backward(grid, q[:, :n], lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3", gy, gj)
+    ggrid, gW, gB, _ = jets.raw_backward(grid, q[:, :n], lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3", gy, gj)
     rgrid, rW, rB = reference_grads(grid, q[:, :n], lo, hi, Ws, bs, "softplus", 1.0, spec, gy, gj)
     errs = {"grid": rel_linf(ggrid.cpu().numpy(), rgrid.cpu().numpy())}
     for l in range(6):

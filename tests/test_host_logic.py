@@ -241,6 +241,42 @@ def test_training_gradients_match_autograd_port(cpu_backend):
         assert rel_linf(model.fc[i].bias.grad.numpy(), port.layers[i].bias.grad.numpy()) < 1e-4, i
 
 
+def test_post_processed_forward_method_stays_twice_differentiable(cpu_backend):
+    """A forward method that post-processes the fused output (here: 2*y - y) takes the autograd route of the
+    reference; dif(dif(y, x), x) and loss.backward() must then work exactly as with the reference modules
+    (the custom backward returned graph-less first derivatives)."""
+    from oracle import jet_oracle as jo
+    from oracle import ref_port as rp
+
+    c = load_case("rb2_softplus")
+    model = build_model(c, 4)
+    grid = torch.tensor(c["grid"], requires_grad=True)
+    q = torch.tensor(c["q"][:, :96])
+    layer = sp.get_rb2_pde_layer(**RB2_CASES["rb2_softplus"])
+
+    def fwd(pts):
+        out = sp.query_local_implicit_grid(model, grid, pts, 0., 1.)
+        return 2.0 * out - out
+
+    layer.update_forward_method(fwd)
+    y, res = layer(q)
+    assert all(v.requires_grad for v in res.values())
+    loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+    loss.backward()
+
+    port = rp.SkipMLP(c["Ws"], c["bs"], "softplus")
+    grid2 = torch.tensor(c["grid"], requires_grad=True)
+    iv, ov, eqs = jo.rb2_equations(**RB2_CASES["rb2_softplus"])
+    y2, res2 = rp.values_and_residuals(port, grid2, q, 0., 1., iv, ov, rp.compile_equations(eqs))
+    loss2 = y2.abs().mean() + 0.0125 * torch.stack(list(res2.values())).abs().mean()
+    loss2.backward()
+    for k in res:
+        assert rel_linf(res[k].detach().numpy(), res2[k].detach().numpy()) < 1e-5, k
+    assert rel_linf(grid.grad.numpy(), grid2.grad.numpy()) < 1e-4
+    for i in range(6):
+        assert rel_linf(model.fc[i].weight.grad.numpy(), port.layers[i].weight.grad.numpy()) < 1e-4, i
+
+
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_torch_jet_checker_gradients_match_reference_golden(name, cpu_backend):
     """Pins the CHECKER of the GPU backward tests: loss.backward() through the jet route with the torch-op jet

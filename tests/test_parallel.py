@@ -58,3 +58,56 @@ def test_two_rank_step_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert abs(mean - ref) < 1e-6 and gerr < 1e-6
+
+
+def _ddp_worker(rank, world, port, out):
+    """DDP(ImNet) through the fused route (torch stand-in backend on CPU): the decoder gradients must come out
+    identical on both ranks and equal to the average of the per-rank gradients, as DDP's reducer would give
+    (reference experiments/rb2d/train_ddp.py: imnet = DDP(imnet))."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import space_time_pde_b200 as sp
+    from space_time_pde_b200 import _torch_jets, jets
+
+    jets.set_test_backend(lambda grid, q, lo, hi, Ws, bs, act, beta, spec: _torch_jets.query_jets(
+        grid, q, lo, hi, list(Ws), list(bs), act, torch.tensor(beta), spec))
+    torch.manual_seed(0)
+    imnet = sp.ImNet(dim=3, in_features=8, out_features=4, nf=4, activation=sp.NONLINEARITIES["softplus"])
+    ddp = torch.nn.parallel.DistributedDataParallel(imnet)
+    grid = torch.randn(1, 3, 4, 5, 8) * 0.5
+    gen = torch.Generator().manual_seed(100 + rank)            # different points per rank
+    q = torch.rand(1, 64, 3, generator=gen)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+
+    def local_loss(model):
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        y, res = layer(q)
+        return y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+
+    local_loss(ddp).backward()
+    got = torch.cat([p.grad.reshape(-1) for p in imnet.parameters()]).clone()
+    imnet.zero_grad()
+    local_loss(imnet).backward()                                 # no wrapper: purely local gradients
+    want = torch.cat([p.grad.reshape(-1) for p in imnet.parameters()]).clone()
+    dist.all_reduce(want)
+    want /= world
+    gathered = [torch.zeros_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    if rank == 0:
+        out.put((float((gathered[0] - gathered[1]).abs().max()), float((got - want).abs().max() / want.abs().max())))
+    dist.destroy_process_group()
+
+
+def test_ddp_wrapped_decoder_gradients_are_averaged_across_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    across, err = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert across == 0.0 and err < 1e-6
