@@ -14,11 +14,11 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libstpde.so")
+LIB_PATH = os.environ.get("STPDE_LIB_PATH") or os.path.join(HERE, "libstpde.so")   # (override: kernel experiments)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["api.cu", "simt_kernels.cu", "bwd_kernels.cu", "tc_path.cu", "tc_bwd.cu", "tc_layers_a.cu", "tc_layers_b.cu",
-           "tc_layers_c.cu", "tc_bwd_a.cu", "tc_bwd_b.cu", "tc_bwd_c.cu", "profile.cu"]
+           "tc_bwd_a.cu", "tc_bwd_b.cu", "tc_bwd_c.cu", "profile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

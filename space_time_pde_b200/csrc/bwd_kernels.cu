@@ -393,12 +393,10 @@ static int launch_blend_backward_t(const JetSpec& spec, const BlendBwdArgs& a_in
     a.acc_copies = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim, 8) <= 96 * 1024 ? 8 : 1;   // 2 CTAs / SM stay resident
     const size_t smem = blend_backward_smem(KC, a.O, a.Kp, a.ld_out, a.dim, a.acc_copies);
     if (smem > 200 * 1024) return STPDE_EUNSUPPORTED;
-    static unsigned long long configured = 0;
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         cudaFuncSetAttribute(blend_backward_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     blend_backward_kernel<KC><<<(a.rows + 127) / 128, 256, smem, st>>>(spec, a);
     return STPDE_OK;

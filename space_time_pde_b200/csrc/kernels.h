@@ -5,7 +5,26 @@
 
 #include "common.cuh"
 
+#include <atomic>
+
 namespace stpde {
+
+// One-time per-device configuration flag (cudaFuncSetAttribute is per device).  The mask is atomic: launch wrappers may
+// be entered from several host threads (one per device / stream); a duplicated attribute call is harmless.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool first_use() const {
+        int d = 0;
+        cudaGetDevice(&d);
+        return !((mask.load(std::memory_order_acquire) >> (d & 63)) & 1ull);
+    }
+    void mark() {
+        int d = 0;
+        cudaGetDevice(&d);
+        mask.fetch_or(1ull << (d & 63), std::memory_order_release);
+    }
+};
+
 
 // Per-chunk scratch arrays (device pointers) produced by prep_points.
 struct ChunkBuffers {

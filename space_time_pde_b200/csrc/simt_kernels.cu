@@ -696,12 +696,10 @@ static void launch_gemm_t(const JetSpec& spec, int dim, int act, float beta, int
                           int NpOut, const float* actIn, const float* Wh, const float* Wx, const float* Vb,
                           int ncat, int cat_off, const int* vtx, const float* xrel, float* out, cudaStream_t st) {
     size_t smem = (size_t)(2 * KC * kBM * kLd + 2 * kBN * kLd) * sizeof(float);
-    static unsigned long long configured = 0;   // bit per device: function attributes are per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         cudaFuncSetAttribute(layer_gemm_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     dim3 grid_dim((NpOut + kBN - 1) / kBN, (rows + kBM - 1) / kBM);
     layer_gemm_kernel<KC><<<grid_dim, 256, smem, st>>>(spec, dim, act, beta, rows, N, Np, Kp, NpOut, actIn, Wh, Wx,
@@ -713,12 +711,10 @@ static void launch_final_t(const JetSpec& spec, int dim, int rows, int pc, int64
                            int O, const float* actIn, const float* Wlast, const float* blast,
                            const ChunkBuffers& cb, float* y, float* jets, cudaStream_t st) {
     size_t smem = (size_t)(O * Kp + KC * 128 * O) * sizeof(float);
-    static unsigned long long configured = 0;   // bit per device: function attributes are per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         cudaFuncSetAttribute(final_blend_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     final_blend_kernel<KC><<<(rows + 127) / 128, 256, smem, st>>>(spec, dim, rows, pc, total_pts, p0, Kp, O, actIn,
                                                                   Wlast, blast, cb, y, jets);

@@ -8,6 +8,7 @@
 #include "bwd_kernels.h"
 #include "profile.h"
 #include "tc_launch.cuh"
+#include "tc_path.h"
 #include "tc_wgrad.cuh"
 
 namespace stpde {
@@ -69,8 +70,7 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
     if (split_weights) cudaMemsetAsync(tc.absmax, 0, 256, st);
     tc.ld0 = round_up(widths[0], 64);
     tc.n0 = widths[0];
-    const char* pair_env = getenv("STPDE_TC_PAIR");
-    tc.use_pair_wide = pair_env ? atoi(pair_env) : 1;
+    tc.use_pair_wide = tc_env().use_pair;
 
     // chunk planes
     char* p = chunk_ws;
@@ -152,9 +152,7 @@ static void base_args(tc::LayerArgs& a, const TcBwdContext& tc, int dim, int act
     a.vtx = cb.vtx;
     a.xrel = cb.xrel;
     a.status = tc.status;
-    a.fast_act = 1;
-    const char* w = getenv("STPDE_WAIT_NS");
-    a.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u;
+    a.wait_ns = tc_env().wait_ns;
 }
 
 int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
@@ -183,9 +181,12 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
         a.out_f32 = act_last;
         a.z_out = L.z;
         a.ldz = L.ldz;
+        int rc = L.last ? tc_encode_out_maps(a, spec.kc, act_last, nullptr, true)
+                        : tc_encode_out_maps(a, spec.kc, a.out_hi, tc.passes == 3 ? (void*)a.out_lo : nullptr, false);
+        if (rc) return rc;
         ProfScope ps(kSlotGemm + l - 1, st);
         // features >= 256: CTA-pair tile (M = 256); narrower layers: one 128-feature CTA per SM
-        int rc = L.n_feat >= 2 * tc::kTileF && tc.use_pair_wide
+        rc = L.n_feat >= 2 * tc::kTileF && tc.use_pair_wide
                      ? tc_launch_pair_save(spec.kc, tc.num_sms, L.w_hi, L.w_lo, L.fa_hi, L.fa_lo, spec, a, st)
                      : tc_launch_single_save(spec.kc, tc.num_sms, L.w_hi, L.w_lo, L.fa_hi, L.fa_lo, spec, a, st);
         if (rc) return rc;
@@ -228,13 +229,11 @@ static int launch_wgrad(const TcBwdContext& tc, const TcBwdLayer& L, float* gW, 
     a.ldw = ldw;
     a.status = tc.status;
     const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
-    static unsigned long long configured = 0;
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         if (cudaFuncSetAttribute(tc::tc_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_wgrad_pair_kernel) failed");
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     const int n_units = a.n_ft * a.n_gt * a.n_slices;
     const int n_pairs = n_units < n_pairs_max ? n_units : n_pairs_max;

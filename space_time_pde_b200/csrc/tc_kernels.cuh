@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,6 +31,34 @@ constexpr int kEpiWarps = 16;   // epilogue warps (4 per TMEM lane quarter, inte
 constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ residual)
+
+// Output staging of the epilogue: every epilogue warp owns one smem buffer holding stage_rows(KC) rows x KC
+// components x 32 features of BOTH fp16 planes (or of the fp32 plane of the last hidden layer) - 128 bytes per
+// (row, component) - which leaves the SM through one cp.async.bulk.tensor store per plane.  Sized so that the
+// operand ring of the single-CTA kernel (2 stages) and the staging of its 16 epilogue warps fit 227 KB.
+#ifndef STPDE_EPI_DIRECT
+#define STPDE_EPI_DIRECT 0      // 1: the forward epilogue stores straight to global memory (no staging, no TMA store)
+#endif
+#ifndef STPDE_EPI_DRAIN
+#define STPDE_EPI_DRAIN 0       // 1: the staging buffer is drained by the warp itself (LDS.128 + STG.128), no TMA store
+#endif
+#ifndef STPDE_EPI_NBUF
+#define STPDE_EPI_NBUF 1        // staging buffers per epilogue warp (2: a pass only waits for the store two passes back)
+#endif
+#ifndef STPDE_EPI_SR_DIV
+#define STPDE_EPI_SR_DIV 1      // divides the rows per staging pass
+#endif
+constexpr int kEpiBuffers = STPDE_EPI_NBUF;
+constexpr uint32_t kRowScratch = 192;   // per epilogue warp: 8 rows x (x_0..x_3) + 8 vertex indices (160 B, padded)
+__host__ __device__ constexpr int stage_rows_base(int kc) {
+    return kc == 1 ? 8 : (kc == 2 || kc == 3 || kc == 6 || kc == 9) ? 4 : kc == 8 ? 1 : 2;
+}
+__host__ __device__ constexpr int stage_rows(int kc) {
+    return stage_rows_base(kc) / STPDE_EPI_SR_DIV > 0 ? stage_rows_base(kc) / STPDE_EPI_SR_DIV : 1;
+}
+__host__ __device__ constexpr uint32_t epi_stage_bytes(int kc) {
+    return STPDE_EPI_DIRECT ? 0u : (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;
+}
 
 // rows (point, corner) per tile for KC jet components: NR % 16 == 0 and KC * NR <= 256
 __host__ __device__ constexpr int rows_per_tile(int kc) {
@@ -101,6 +131,60 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// smem -> global tensor store (bulk async group of the issuing thread); the box is clipped at the tensor bounds
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)m), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// shared-space accesses of the staging buffers (a generic pointer makes the compiler emit generic ST / LD)
+__device__ __forceinline__ void sts_b16(uint32_t addr, __half v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(v)) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// the same with a compile-time byte offset inside the instruction (st.shared [base + imm])
+template <int OFF>
+__device__ __forceinline__ void sts_b16_o(uint32_t base, __half v) {
+    asm volatile("st.shared.b16 [%0+%2], %1;" ::"r"(base), "h"(__half_as_ushort(v)), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f32_o(uint32_t base, float v) {
+    asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(base), "f"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ uint4 lds_v4_o(uint32_t base) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base), "n"(OFF) : "memory");
+    return v;
+}
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{})
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+// generic-proxy smem writes -> visible to the async proxy (TMA store / UMMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -168,11 +252,6 @@ struct LayerArgs {
     int passes;        // 3 = hi/lo split, 1 = single fp16 pass
     int dim, act, ncat, cat_off;
     float beta;
-    int fast_act;          // 1: MUFU-based activation jets, 0: libdevice-accurate
-    int n0;                // GEN mode: true width of layer 0 (= K of this layer before padding)
-    int vb_vec;            // GEN mode: Vb rows may be read with 16-byte loads
-    const float* wx0p;     // GEN mode: layer-0 coordinate columns, [kp_in][4] zero padded
-    const float* coef0;    // GEN mode: [KC][kp_in] per-feature jet coefficients * 2^4 (0 for pad features)
     const float* wscale;   // device: 2^-(sw_l + sa) for this layer
     const float* Wx;       // [n_feat][dim]
     const float* Vb;       // [nvert][ncat]
@@ -191,6 +270,9 @@ struct LayerArgs {
     int g_wx_ld;
     float* g_beta;         // MODE 2/3: adjoint of the Swish beta (atomics), may be null
     uint32_t wait_ns;      // suspend-time hint of the mbarrier waits (pair kernel)
+    // TMA store maps of the output planes (dims (ld_out, rows, KC), box 32 features x stage_rows(KC) rows x KC):
+    // [0] = fp16 hi plane, or the fp32 plane of the last hidden layer; [1] = fp16 lo plane (3-pass mode only)
+    CUtensorMap out_map[2];
 };
 
 // Static jet specifications (template parameter SPEC): 0 = generic (runtime JetSpec), 1 = the Rayleigh-Benard set
@@ -454,22 +536,278 @@ __device__ __forceinline__ void bwd_epilogue_tile(const JetSpec& spec, const Lay
     if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
 }
 
+
+// One tile of the forward epilogue (shared by the CTA-pair and the single-CTA kernel): TMEM -> skip term + jet
+// activation -> next layer's operand planes.
+//   * thread = output feature g (TMEM lane), 8-row blocks rb = sub, sub + EPI_PQ, ... of the tile per warp;
+//   * the per-row operands of the skip term (vertex index, cell-local coordinates) are fetched by ONE coalesced
+//     load per lane and 8-row block into a 160-byte smem scratch and read back as broadcasts (they were 4-5 global
+//     loads with 64-bit address arithmetic per (row, feature));
+//   * the accumulator buffer is handed back right after the last tcgen05.wait::ld of the warp - before any math -
+//     with release semantics (no global store of this tile is outstanding at that point);
+//   * results go to the warp's smem staging buffer with immediate-offset 2-byte stores (st.shared [base + imm]: no
+//     address arithmetic per element), SR rows at a time, and leave either through cp.async.bulk.tensor (TMA) stores -
+//     the tensor map clips rows / features at the plane bounds - or (STPDE_EPI_DRAIN) through 16-byte loads / stores
+//     of the same warp.
+// OUTK: 0 = fp16 hi + lo planes (3-pass mode), 1 = fp16 hi plane only (single pass), 2 = fp32 plane (last hidden layer).
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class HandBack>
+__device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
+                                                  uint32_t row_addr, int f0, int r0, int quarter, int sub, int lane,
+                                                  uint32_t taddr, uint32_t tfull_addr, uint32_t tfull_parity,
+                                                  HandBack&& hand_back) {
+    constexpr int SR = stage_rows(KC);
+    constexpr int NBUF = kEpiBuffers;
+    constexpr int NPASS = 8 / SR;
+    const int fw = f0 + quarter * 32;                         // first feature of this warp
+    const int g = fw + lane;
+    const bool g_ok = g < args.n_feat;
+    if (!(fw < args.n_store && sub < NRB)) {                  // warp-uniform: nothing to do in this tile
+        mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
+        hand_back();
+        return;
+    }
+    const float scale = __ldg(args.wscale);
+    // pad features [n_feat, n_store) are written as zeros; fp16 planes carry a * 2^4
+    const float sm = g_ok ? (OUTK == 2 ? 1.f : (float)(1 << kActScaleLog2)) : 0.f;
+    const int n_first = spec.n_first;
+    float wx[kMaxDim];
+#pragma unroll
+    for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+    float wxc[KC];                                            // constant tangent seed of first-order components
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        wxc[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k)
+            if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+    }
+    const float* vb_g = args.Vb + args.cat_off + (g_ok ? g : 0);
+    // Row operands of one 8-row block -> smem scratch [8 rows][x_0..x_3] + [8] vertex indices.
+    // lane -> (coordinate plane k = lane / 8, row i = lane % 8); planes >= dim are zero.
+    auto stage_rows_of = [&](int rbase) {
+        const int rr = min(rbase + (lane & 7), args.rows - 1);
+        const float xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
+        const int vv = __ldg(args.vtx + rr);
+        __syncwarp();                                           // earlier readers of the scratch are done
+        sts_f32(row_addr + (lane & 7) * 16 + (lane >> 3) * 4, xv);
+        if (lane < 8) sts_f32(row_addr + 128 + lane * 4, __int_as_float(vv));
+        __syncwarp();
+    };
+    // skip connection + per-vertex latent/bias term of the 8 rows (independent loads, issued early)
+    auto skip_terms = [&](float* zs) {
+        static_for<8>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const uint4 x = lds_v4(row_addr + i * 16);
+            const int vt = (int)lds_b32(row_addr + 128 + i * 4);
+            float z = g_ok ? __ldg(vb_g + (int64_t)vt * args.ncat) : 0.f;
+            z = fmaf(wx[0], __uint_as_float(x.x), z);
+            z = fmaf(wx[1], __uint_as_float(x.y), z);
+            z = fmaf(wx[2], __uint_as_float(x.z), z);
+            z = fmaf(wx[3], __uint_as_float(x.w), z);
+            zs[i] = z;
+        });
+    };
+    float zs[8];
+    stage_rows_of(r0 + sub * 8);
+    skip_terms(zs);
+    mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
+    tc_fence_after();
+    float amax = 0.f;
+#pragma unroll 1
+    for (int rb = sub; rb < NRB; rb += EPI_PQ) {
+        const int rbase = r0 + rb * 8;
+        uint32_t v[KC][8];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
+        const bool more = rb + EPI_PQ < NRB;
+        tmem_wait_ld();
+        if (!more) hand_back();                               // the accumulator values of this warp are in registers
+        dispatch_act(args.act, [&](auto act_c) {
+        constexpr int kAct = decltype(act_c)::value;
+        static_for<NPASS>([&](auto PS) {
+            constexpr int ps = decltype(PS)::value;
+            float o[SR][KC];
+#pragma unroll
+            for (int ir = 0; ir < SR; ++ir) {
+                const int i = ps * SR + ir;
+                float zt[KC];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
+                const float z0 = zt[0] + zs[i];
+                float s0, s1, s2;
+                act_jet_fast(kAct, args.beta, z0, s0, s1, s2);
+                if constexpr (MODE == kModeFwdSave) {
+                    const int r = rbase + i;
+                    if (g_ok && r < args.rows) {               // pre-activations for the reverse sweep
+                        const int64_t zplane = (int64_t)args.rows * args.ldz;
+                        float* pz = args.z_out + (int64_t)r * args.ldz + g;
+                        *pz = z0;
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
+                    }
+                }
+                s0 *= sm; s1 *= sm; s2 *= sm;
+                o[ir][0] = s0;
+                if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                    o[ir][1] = s1 * zt[1]; o[ir][2] = s1 * zt[2]; o[ir][3] = s1 * zt[3];
+                    o[ir][4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
+                    o[ir][5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
+                } else {
+#pragma unroll
+                    for (int c = 1; c < KC; ++c) {
+                        float oc = s1 * zt[c];
+                        if (c > n_first) {                   // second order (warp-uniform): parents za, zb
+                            float za = 0.f, zb = 0.f;
+#pragma unroll
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                if (1 + k < KC) {
+                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                }
+                            }
+                            oc = fmaf(s2 * za, zb, oc);
+                        }
+                        o[ir][c] = oc;
+                    }
+                }
+            }
+#if STPDE_EPI_DIRECT
+            // (experiment) direct stores with 64-bit address arithmetic per element
+#pragma unroll
+            for (int ir = 0; ir < SR; ++ir) {
+                const int r = rbase + ps * SR + ir;
+                if (r < args.rows && g < args.n_store) {
+                    const size_t off = ((size_t)r * args.ld_out + g) * (OUTK == 2 ? 4u : 2u);
+                    const size_t plane_b = (size_t)args.rows * args.ld_out * (OUTK == 2 ? 4 : 2);
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) {
+                        const float xs = o[ir][c];
+                        if constexpr (OUTK == 2) {
+                            *reinterpret_cast<float*>(reinterpret_cast<char*>(args.out_f32) + c * plane_b + off) = xs;
+                        } else {
+                            amax = fmaxf(amax, fabsf(xs));
+                            const __half hi = __float2half_rn(xs);
+                            *reinterpret_cast<__half*>(reinterpret_cast<char*>(args.out_hi) + c * plane_b + off) = hi;
+                            if constexpr (OUTK == 0)
+                                *reinterpret_cast<__half*>(reinterpret_cast<char*>(args.out_lo) + c * plane_b + off) =
+                                    __float2half_rn(xs - __half2float(hi));
+                        }
+                    }
+                }
+            }
+#else
+            constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SR * 128) : 0;
+            const uint32_t sb = stg_addr + kBufOff;
+#if !STPDE_EPI_DRAIN
+            // the TMA engine must have read the previous contents of this staging buffer
+            if (lane == 0) { if constexpr (NBUF > 1) bulk_wait_read1(); else bulk_wait_read0(); }
+            __syncwarp();
+#endif
+            {
+                const uint32_t sl = sb + lane * (OUTK == 2 ? 4 : 2);
+                static_for<SR>([&](auto IR) {
+                    static_for<KC>([&](auto C) {
+                        constexpr int ir = decltype(IR)::value, c = decltype(C)::value;
+                        const float xs = o[ir][c];
+                        if constexpr (OUTK == 2) {
+                            sts_f32_o<(c * SR + ir) * 128>(sl, xs);
+                        } else {
+                            amax = fmaxf(amax, fabsf(xs));
+                            const __half hi = __float2half_rn(xs);
+                            sts_b16_o<(c * SR + ir) * 64>(sl, hi);
+                            if constexpr (OUTK == 0)
+                                sts_b16_o<(KC * SR + c * SR + ir) * 64>(sl, __float2half_rn(xs - __half2float(hi)));
+                        }
+                    });
+                });
+            }
+#if STPDE_EPI_DRAIN
+            // drain the staging buffer with 16-byte loads / stores: lane -> (staged row = lane / LPR + k * (32 / LPR),
+            // 16-byte part = lane % LPR); a staged row is one (component, row) run of 32 features
+            __syncwarp();
+            {
+                constexpr int EB = OUTK == 2 ? 4 : 2;                    // bytes per element
+                constexpr int LPR = 32 * EB / 16;                       // lanes per staged row (4 or 8)
+                constexpr int RPI = 32 / LPR;                           // staged rows per warp instruction
+                constexpr int NPL = OUTK == 0 ? 2 : 1;                  // planes
+                const int part = lane % LPR;
+                const bool f_in = fw + part * (16 / EB) < args.n_store;
+                const size_t plane_b = (size_t)args.rows * args.ld_out * EB;
+                const uint32_t sl = sb + (lane / LPR) * (32 * EB) + part * 16;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    char* gbase = (OUTK == 2 ? reinterpret_cast<char*>(args.out_f32)
+                                             : reinterpret_cast<char*>(pl ? args.out_lo : args.out_hi)) +
+                                  ((size_t)fw * EB + part * 16);
+                    static_for<(KC * SR + RPI - 1) / RPI>([&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        const int srow = lane / LPR + k * RPI;          // staged row: c * SR + ir
+                        const int c = srow / SR, ir = srow % SR;
+                        const int r = rbase + ps * SR + ir;
+                        if (srow < KC * SR && r < args.rows && f_in) {
+                            const uint4 val = pl ? lds_v4_o<KC * SR * 64 + k * RPI * 32 * EB>(sl) : lds_v4_o<k * RPI * 32 * EB>(sl);
+                            *reinterpret_cast<uint4*>(gbase + c * plane_b + (size_t)r * args.ld_out * EB) = val;
+                        }
+                    });
+                }
+            }
+            __syncwarp();                                               // the buffer is free again
+#else
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&args.out_map[0], sb, fw, rbase + ps * SR, 0);
+                if constexpr (OUTK == 0) tma_store_3d(&args.out_map[1], sb + KC * SR * 64, fw, rbase + ps * SR, 0);
+                bulk_commit();
+            }
+#endif
+#endif
+        });
+        });
+        if (more) {
+            stage_rows_of(r0 + (rb + EPI_PQ) * 8);
+            skip_terms(zs);
+        }
+    }
+    if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+}
+
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class HandBack>
+__device__ __forceinline__ void fwd_epilogue_tile(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
+                                                  int f0, int r0, int quarter, int sub, int lane, uint32_t taddr,
+                                                  uint32_t tfull_addr, uint32_t tfull_parity, HandBack&& hand_back) {
+    if (args.last)
+        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 2>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+    else if (args.passes == 3)
+        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+    else
+        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+}
+
+// bytes of output staging a kernel mode needs (all 16 epilogue warps); the reverse modes still store directly
+template <int KC, int MODE>
+__host__ __device__ constexpr uint32_t epi_staging_total() {
+    return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + kRowScratch) : 0u;
+}
+
 template <int KC, int SPEC = 0, int MODE = kModeFwd>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                JetSpec spec, LayerArgs args) {
+                const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
     constexpr int NR = rows_per_tile(KC);
     constexpr int N = KC * NR;
     constexpr int NRB = NR / 8;
     constexpr uint32_t kWBytes = kTileF * kBlockK * 2;        // one W plane tile
     constexpr uint32_t kABytes = N * kBlockK * 2;             // one activation plane tile
     constexpr uint32_t kStageBytes = 2 * kWBytes + 2 * kABytes;
+    constexpr uint32_t kStaging = epi_staging_total<KC, MODE>();
     constexpr uint32_t kTmemCols = 512;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+    uint8_t* staging = smem + kStages * kStageBytes;
+    uint64_t* bars = (uint64_t*)(staging + kStaging);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tfull_bar = bars + 2 * kStages;
@@ -486,11 +824,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        if (MODE < kModeBwd) { tma_prefetch_desc(&args.out_map[0]); tma_prefetch_desc(&args.out_map[1]); }
     }
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 32 * kEpiWarps); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -559,148 +898,39 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (MODE >= kModeBwd) {
-        // ===================== reverse-mode epilogue (bwd_epilogue_tile) =====================
-        const int quarter = warp & 3;
-        const int sub = (warp - 2) >> 2;
-        int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-            const int tn = t + gridDim.x;
-            const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF + quarter * 32 : -1;
-            const int next_r0 = (tn / n_ftiles) * NR;
-            bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane,
-                                                                   tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N,
-                                                                   smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
-            tc_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[buf]));
-        }
     } else {
-        // ===================== epilogue warps: TMEM -> jets activation -> global =====================
-        // Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter alternate 8-row blocks.
+        // ===================== epilogue warps =====================
+        // Warp w may only touch TMEM lanes 32*(w%4)..+31; the warps of a quarter take the 8-row blocks in turn.
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
-        const float scale = __ldg(args.wscale);
-        const float act_scale = (float)(1 << kActScaleLog2);
-        const int n_first = spec.n_first;
-        // skip connection + per-vertex latent/bias term of one 8-row block (independent loads, issued early)
-        auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = min(r_base + i, args.rows - 1);
-                float z = (g < args.n_feat) ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + r) * args.ncat + args.cat_off + g) : 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < args.dim) z = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + r), z);
-                zs[i] = z;
-            }
-        };
-        const int64_t plane = (int64_t)args.rows * args.ld_out;   // elements between jet components
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
             const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-            const int g = f0 + quarter * 32 + lane;
-            const bool g_store = g < args.n_store;
-            const float fmask = g < args.n_feat ? 1.f : 0.f;       // pad features are written as zeros
-            float wx[kMaxDim];
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
-            float wxc[KC];                                          // constant tangent seed of first-order components
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                wxc[c] = 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
-            }
-            float zs[8];
-            if (sub < NRB) load_skip(r0 + sub * 8, g, wx, zs);
-            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            float amax = 0.f;
-#pragma unroll 1
-            for (int rb = sub; rb < NRB; rb += kEpiPerQuarter) {
-                uint32_t v[KC][8];
-#pragma unroll
-                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
-                float zs_next[8];
-                if (rb + kEpiPerQuarter < NRB) load_skip(r0 + (rb + kEpiPerQuarter) * 8, g, wx, zs_next);
-                tmem_wait_ld();
-                dispatch_act(args.act, [&](auto act_c) {
-                constexpr int kAct = decltype(act_c)::value;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + rb * 8 + i;
-                    float zt[KC], o[KC];
-#pragma unroll
-                    for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
-                    float s0, s1, s2;
-                    act_jet_fast(kAct, args.beta, zt[0] + zs[i], s0, s1, s2);
-                    if constexpr (MODE == kModeFwdSave) {
-                        if (g < args.n_feat && r < args.rows) {     // pre-activations for the reverse sweep
-                            const int64_t zplane = (int64_t)args.rows * args.ldz;
-                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
-                            *pz = zt[0] + zs[i];
-#pragma unroll
-                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
-                        }
-                    }
-                    o[0] = s0 * fmask;
-                    s1 *= fmask;
-                    s2 *= fmask;
-                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
-                        o[1] = s1 * zt[1]; o[2] = s1 * zt[2]; o[3] = s1 * zt[3];
-                        o[4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
-                        o[5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
-                    } else {
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) {
-                            o[c] = s1 * zt[c];
-                            if (c > n_first) {               // second order (warp-uniform): parents za, zb
-                                float za = 0.f, zb = 0.f;
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                    if (1 + k < KC) {
-                                        za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                        zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
-                                    }
-                                }
-                                o[c] = fmaf(s2 * za, zb, o[c]);
-                            }
-                        }
-                    }
-                    if (g_store && r < args.rows) {
-                        const int64_t off = (int64_t)r * args.ld_out + g;
-                        if (args.last) {
-                            float* pf = args.out_f32 + off;
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) { *pf = o[c]; pf += plane; }
-                        } else {
-                            __half* ph = args.out_hi + off;
-                            __half* pl = args.out_lo + off;
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) {
-                                const float xs = o[c] * act_scale;
-                                amax = fmaxf(amax, fabsf(xs));
-                                const __half hi = __float2half_rn(xs);
-                                *ph = hi;
-                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
-                                ph += plane; pl += plane;
-                            }
-                        }
-                    }
-                }
-                });
-#pragma unroll
-                for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
+            const uint32_t tempty = smem_u32(&tempty_bar[buf]);
+            // TMEM hand-back: the tcgen05.ld results are in registers (tcgen05.wait::ld), ordered before the arrive
+            auto hand_back = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
+            };
+            if constexpr (MODE >= kModeBwd) {
+                const int tn = t + gridDim.x;
+                const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF + quarter * 32 : -1;
+                const int next_r0 = (tn / n_ftiles) * NR;
+                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, taddr,
+                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
+                hand_back();
+            } else {
+                fwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args,
+                                                                       smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+                                                                       smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
+                                                                       f0, r0, quarter, sub, lane, taddr,
+                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, hand_back);
             }
-            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
-            tc_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[buf]));
         }
+        if (MODE < kModeBwd && lane == 0) bulk_wait0();        // staging must stay valid until the last store has read it
     }
     tc_fence_before();
     __syncthreads();
@@ -711,14 +941,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
 // =============================================================================================
 // CTA-pair version (cta_group::2): two SMs of a cluster share one 256-feature x N tile.
 //   * each CTA TMA-loads its own 128 weight rows and its own HALF of the activation rows, so the
-//     per-SM operand traffic and smem footprint drop (4+ pipeline stages instead of 2);
+//     per-SM operand traffic and smem footprint drop (3+ pipeline stages instead of 2);
 //   * the leader CTA (cluster rank 0) issues every tcgen05.mma.cta_group::2 (M = 256); the
 //     accumulator rows 0..127 land in the leader's TMEM, rows 128..255 in the peer's;
 //   * full barriers live in the leader (both CTAs' TMA traffic completes on them), empty / tmem-full
 //     barriers are multicast to both CTAs by tcgen05.commit, tmem-empty arrivals go to the leader.
 // =============================================================================================
 constexpr int kPairMaxStages = 8;
-constexpr uint32_t kPairSmemBudget = 224 * 1024;
+constexpr uint32_t kPairSmemBudget = 224 * 1024;            // operand ring + output staging
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -737,10 +967,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Same without release semantics: the epilogue only hands the TMEM accumulator back (its tcgen05.ld results are
-// already in registers after tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The releasing form makes the
-// warp drain every global store / red of the tile first (MEMBAR.ALL.GPU + ERRBAR: ~8 % of the epilogue's stall
-// samples and the tile's TMEM buffer stays blocked for the whole drain).
+// Same without release semantics, for the reverse-mode epilogue only: it hands the accumulator back AFTER the tile's
+// global stores / reds were issued, and the releasing form would drain them first (MEMBAR.ALL.GPU + ERRBAR, ~8 % of
+// that epilogue's stall samples).  Its tcgen05.ld results are in registers (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync) long before the arrive; the forward epilogue uses the release form.
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -777,15 +1007,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
         : "memory");
 }
 
-// GEN = true fuses layer 0 into this (layer 1) kernel: the activation operand tiles are not TMA-loaded from HBM
-// planes but GENERATED in shared memory by 8 generator warps from the closed-form layer-0 jets
-// (a_c = sigma^(k)(z0) * coef_c, z0 = Vb0[vertex] + W0x . x_rel), written in the SWIZZLE_128B K-major layout the
-// UMMA descriptors expect.  This removes layer 0's HBM round trip (412 GB / step at BASELINE config 2).
-template <int KC, bool GEN, int MODE = kModeFwd, int SPEC = 0>
+template <int KC, int MODE = kModeFwd, int SPEC = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                     JetSpec spec, LayerArgs args) {
+                     const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
     constexpr int NR = rows_per_tile(KC);
     constexpr int N = KC * NR;
     constexpr int NRB = NR / 8;
@@ -793,16 +1019,16 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     constexpr int kTileF2 = 2 * kTileF;
     constexpr uint32_t kWBytes = kTileF * kBlockK * 2;          // one W plane tile of this CTA (128 rows)
     constexpr uint32_t kABytes = (N / 2) * kBlockK * 2;         // this CTA's half of one activation plane tile
+    constexpr uint32_t kStaging = epi_staging_total<KC, MODE>();
+    constexpr uint32_t kRingBudget = kPairSmemBudget - kStaging;
     constexpr uint32_t kTmemCols = 512;
-    constexpr int kEpiW = GEN ? 8 : kEpiWarps;                  // epilogue warps (rest of the CTA generates in GEN mode)
-    constexpr int kEpiPQ = kEpiW / 4;
-    constexpr int kGenWarps = 8, kGenPerStage = kGenWarps / 2;  // two sets of 4 warps alternate K blocks
     const bool three = args.passes == 3;
     const uint32_t stage_bytes = three ? 2 * kWBytes + 2 * kABytes : kWBytes + kABytes;
-    const int n_stages = min((int)(kPairSmemBudget / stage_bytes), kPairMaxStages);
+    const int n_stages = min((int)(kRingBudget / stage_bytes), kPairMaxStages);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* staging = smem + kRingBudget;
     uint64_t* bars = (uint64_t*)(smem + kPairSmemBudget);
     uint64_t* full_bar = bars;                                  // used in the leader only
     uint64_t* empty_bar = bars + kPairMaxStages;                // one copy per CTA
@@ -822,12 +1048,12 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        if (MODE < kModeBwd) { tma_prefetch_desc(&args.out_map[0]); tma_prefetch_desc(&args.out_map[1]); }
     }
     if (warp == 1) {
         if (lane == 0) {
-            // full: the leader's expect_tx arrival (+ one arrival per generator warp of BOTH CTAs in GEN mode)
-            for (int s = 0; s < kPairMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), GEN ? 1 + 2 * kGenPerStage : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiW); }
+            for (int s = 0; s < kPairMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -850,17 +1076,14 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 const uint32_t base = smem_u32(smem + stage * stage_bytes);
                 const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
                 if (elect_one()) {
-                    const uint32_t tx = GEN ? (three ? 2 * kWBytes : kWBytes) : stage_bytes;    // TMA bytes per CTA
-                    if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * tx);            // bytes of BOTH CTAs
+                    if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * stage_bytes);   // bytes of BOTH CTAs
                     tma_load_2d_pair(base, &map_w_hi, kb * kBlockK, f0, fb);
                     if (three) tma_load_2d_pair(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
-                    if (!GEN) {
 #pragma unroll
-                        for (int rb = 0; rb < NRB / 2; ++rb) {
-                            tma_load_3d_pair(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
-                            if (three)
-                                tma_load_3d_pair(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
-                        }
+                    for (int rb = 0; rb < NRB / 2; ++rb) {
+                        tma_load_3d_pair(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        if (three)
+                            tma_load_3d_pair(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
                     }
                 }
                 __syncwarp();
@@ -903,249 +1126,40 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 }
             }
         }
-    } else if (GEN && warp >= 2 + kEpiW) {
-        // ===================== generator warps: layer-0 jets -> swizzled K-major operand tiles in smem =====================
-        const int gw = warp - (2 + kEpiW);
-        const int set = gw / kGenPerStage;                       // this warp serves K blocks of this parity
-        const int t128 = (gw % kGenPerStage) * 32 + lane;
-        constexpr int kItems = (NR / 2) * 8;                     // (local row, 16-byte chunk of 8 features)
-        constexpr int kPerThread = (kItems + 32 * kGenPerStage - 1) / (32 * kGenPerStage);
-        int stage = 0; uint32_t phase = 0;
-        uint32_t gcount = 0;
-        for (int t = pair_id; t < n_tiles; t += n_pairs) {
-            const int r0 = (t / n_ftiles) * NR + (int)rank * (NR / 2);
-            // per-item row data is the same for every K block of the tile
-            int vrow[kPerThread];
-            float xr[kPerThread][kMaxDim];
-            bool rok[kPerThread];
-#pragma unroll
-            for (int q = 0; q < kPerThread; ++q) {
-                const int item = t128 + q * 32 * kGenPerStage;
-                const int r = r0 + (item >> 3);
-                rok[q] = item < kItems && r < args.rows;
-                const int rc = min(r, args.rows - 1);
-                vrow[q] = __ldg(args.vtx + rc);
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k) xr[q][k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
-            }
-            for (int kb = 0; kb < kb_count; ++kb, ++gcount) {
-                if ((gcount & 1u) == (uint32_t)set) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status, args.wait_ns);
-                    uint8_t* a_tile = smem + stage * stage_bytes + (three ? 2 * kWBytes : kWBytes);
-#pragma unroll
-                    for (int q = 0; q < kPerThread; ++q) {
-                        const int item = t128 + q * 32 * kGenPerStage;
-                        if (item >= kItems) continue;
-                        const int rl = item >> 3, j = item & 7;
-                        const int f0g = kb * kBlockK + j * 8;
-                        float o[KC][8];
-                        if (rok[q]) {
-                            // tables are padded to the K block: features >= n0 have zero coefficients
-                            const float4* vb4 = reinterpret_cast<const float4*>(args.Vb + (int64_t)vrow[q] * args.ncat + f0g);
-                            const float4* wx4 = reinterpret_cast<const float4*>(args.wx0p) + f0g;
-                            float vb[8];
-                            if (args.vb_vec) {
-                                const float4 a = __ldg(vb4), b = __ldg(vb4 + 1);
-                                vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w; vb[4] = b.x; vb[5] = b.y; vb[6] = b.z; vb[7] = b.w;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) vb[e] = (f0g + e < args.n0) ? __ldg(args.Vb + (int64_t)vrow[q] * args.ncat + f0g + e) : 0.f;
-                            }
-                            float sg[3][8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 w = __ldg(wx4 + e);
-                                float z = vb[e];
-                                z = fmaf(w.x, xr[q][0], z); z = fmaf(w.y, xr[q][1], z);
-                                z = fmaf(w.z, xr[q][2], z); z = fmaf(w.w, xr[q][3], z);
-                                act_jet_fast(args.act, args.beta, z, sg[0][e], sg[1][e], sg[2][e]);
-                            }
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) {
-                                const float4* cf4 = reinterpret_cast<const float4*>(args.coef0 + (int64_t)c * args.kp_in + f0g);
-                                const float4 a = __ldg(cf4), b = __ldg(cf4 + 1);
-                                const float cf[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    o[c][e] = (spec.kind[c] == 0 ? sg[0][e] : spec.kind[c] == 1 ? sg[1][e] : sg[2][e]) * cf[e];
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < KC; ++c)
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) o[c][e] = 0.f;
-                        }
-                        const int rbl = rl >> 3, i = rl & 7;
-#pragma unroll
-                        for (int c = 0; c < KC; ++c) {
-                            uint32_t ph[4], pl[4];
-#pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                const __half2 h = __floats2half2_rn(o[c][e], o[c][e + 1]);
-                                const float2 hf = __half22float2(h);
-                                const __half2 l = __floats2half2_rn(o[c][e] - hf.x, o[c][e + 1] - hf.y);
-                                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-                            }
-                            const uint32_t row = rbl * (8 * KC) + c * 8 + i;                 // row of the operand tile
-                            uint8_t* dst = a_tile + row * 128 + ((j ^ i) << 4);               // SWIZZLE_128B: chunk ^ (row % 8)
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            if (three) *reinterpret_cast<uint4*>(dst + kABytes) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&full_bar[stage]), 0));
-                }
-                if (++stage == n_stages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (MODE >= kModeBwd && warp < 2 + kEpiW) {
-        // ===================== reverse-mode epilogue (bwd_epilogue_tile) =====================
-        const int quarter = warp & 3;
-        const int sub = (warp - 2) >> 2;
-        const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
-        const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
-        int it = 0;
-        for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
-            const int buf = it & 1;
-            const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
-            const int tn = t + n_pairs;
-            const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32 : -1;
-            const int next_r0 = (tn / n_ftiles) * NR;
-            bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPQ>(spec, args, f0, r0, quarter, sub, lane,
-                                                           tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N,
-                                                           smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
-        }
-    } else if (MODE < kModeBwd && warp < 2 + kEpiW) {
+    } else {
         // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
-        const float scale = __ldg(args.wscale);
-        const float act_scale = (float)(1 << kActScaleLog2);
-        const int n_first = spec.n_first;
-        auto load_skip = [&](int r_base, int g, const float* wx, float* zs) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = min(r_base + i, args.rows - 1);
-                float z = (g < args.n_feat) ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + r) * args.ncat + args.cat_off + g) : 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < args.dim) z = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + r), z);
-                zs[i] = z;
-            }
-        };
-        const int64_t plane = (int64_t)args.rows * args.ld_out;
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
         for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
             const int buf = it & 1;
             const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
-            const int g = f0 + quarter * 32 + lane;
-            const bool g_store = g < args.n_store;
-            const float fmask = g < args.n_feat ? 1.f : 0.f;
-            float wx[kMaxDim];
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g < args.n_feat) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
-            float wxc[KC];
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                wxc[c] = 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
-            }
-            float zs[8];
-            if (sub < NRB) load_skip(r0 + sub * 8, g, wx, zs);
-            mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1, args.status, args.wait_ns);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            float amax = 0.f;
-#pragma unroll 1
-            for (int rb = sub; rb < NRB; rb += kEpiPQ) {
-                uint32_t v[KC][8];
-#pragma unroll
-                for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
-                float zs_next[8];
-                if (rb + kEpiPQ < NRB) load_skip(r0 + (rb + kEpiPQ) * 8, g, wx, zs_next);
-                tmem_wait_ld();
-                dispatch_act(args.act, [&](auto act_c) {
-                constexpr int kAct = decltype(act_c)::value;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + rb * 8 + i;
-                    float zt[KC], o[KC];
-#pragma unroll
-                    for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
-                    float s0, s1, s2;
-                    act_jet_fast(kAct, args.beta, zt[0] + zs[i], s0, s1, s2);
-                    if constexpr (MODE == kModeFwdSave) {
-                        if (g < args.n_feat && r < args.rows) {     // pre-activations for the reverse sweep
-                            const int64_t zplane = (int64_t)args.rows * args.ldz;
-                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
-                            *pz = zt[0] + zs[i];
-#pragma unroll
-                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
-                        }
-                    }
-                    o[0] = s0 * fmask;
-                    s1 *= fmask;
-                    s2 *= fmask;
-                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
-                        o[1] = s1 * zt[1]; o[2] = s1 * zt[2]; o[3] = s1 * zt[3];
-                        o[4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
-                        o[5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
-                    } else {
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) {
-                            o[c] = s1 * zt[c];
-                            if (c > n_first) {               // second order (warp-uniform): parents za, zb
-                                float za = 0.f, zb = 0.f;
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                    if (1 + k < KC) {
-                                        za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                        zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
-                                    }
-                                }
-                                o[c] = fmaf(s2 * za, zb, o[c]);
-                            }
-                        }
-                    }
-                    if (g_store && r < args.rows) {
-                        const int64_t off = (int64_t)r * args.ld_out + g;
-                        if (args.last) {
-                            float* pf = args.out_f32 + off;
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) { *pf = o[c]; pf += plane; }
-                        } else {
-                            __half* ph = args.out_hi + off;
-                            __half* pl = args.out_lo + off;
-#pragma unroll
-                            for (int c = 0; c < KC; ++c) {
-                                const float xs = o[c] * act_scale;
-                                amax = fmaxf(amax, fabsf(xs));
-                                const __half hi = __float2half_rn(xs);
-                                *ph = hi;
-                                if (three) *pl = __float2half_rn(xs - __half2float(hi));
-                                ph += plane; pl += plane;
-                            }
-                        }
-                    }
-                }
-                });
-#pragma unroll
-                for (int i = 0; i < 8; ++i) zs[i] = zs_next[i];
+            if constexpr (MODE >= kModeBwd) {
+                const int tn = t + n_pairs;
+                const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32 : -1;
+                const int next_r0 = (tn / n_ftiles) * NR;
+                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, taddr,
+                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
+            } else {
+                auto hand_back = [&]() {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+                };
+                fwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args,
+                                                                       smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+                                                                       smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
+                                                                       f0, r0, quarter, sub, lane, taddr,
+                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, hand_back);
             }
-            if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
         }
+        if (MODE < kModeBwd && lane == 0) bulk_wait0();
     }
     tc_fence_before();
     cluster_sync_all();

@@ -9,8 +9,10 @@ namespace stpde {
 int tc_fail(int code, const char* msg);
 int tc_launch_layer(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 int tc_launch_layer_pair(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
-int tc_launch_layer_pair_gen(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 
+#ifdef STPDE_ONLY_RB2   // kernel experiments (tools/build_variant.sh): instantiate K = 6 only, builds in a fraction of the time
+#define STPDE_TC_DISPATCH_KC(kc, CALL) { constexpr int KC = 6; CALL; }
+#else
 #define STPDE_TC_DISPATCH_KC(kc, CALL)                 \
     switch (kc) {                                      \
         case 1: { constexpr int KC = 1; CALL; } break; \
@@ -24,11 +26,15 @@ int tc_launch_layer_pair_gen(int kc, const TcContext& tc, const TcLayerPlan& L, 
         case 9: { constexpr int KC = 9; CALL; } break; \
         default: { constexpr int KC = 10; CALL; } break; \
     }
+#endif
 
 // Rayleigh-Benard jet set [value | d0, d1, d2 | d11, d22] -> kernels specialised at compile time (tc::kSpecRb2)
 static inline bool spec_is_rb2(const JetSpec& s) {
     return s.kc == 6 && s.n_first == 3 && s.n_second == 2 && s.pa[4] == 2 && s.pb[4] == 2 && s.pa[5] == 3 && s.pb[5] == 3;
 }
+
+// Fills a.out_map for the output planes of a forward layer launch (tc_path.cu).
+int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32);
 
 #ifdef STPDE_TC_LAUNCH_IMPL
 template <int KC, int SPEC = 0>
@@ -36,14 +42,13 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
                         cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     constexpr int N = KC * NR;
-    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
-    static unsigned long long configured = 0;   // bit per device: function attributes are per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) +
+                        tc::epi_staging_total<KC, tc::kModeFwd>() + 1024 + 256;
+    static DeviceOnce configured;               // function attributes are per device
+    if (configured.first_use()) {
         if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel) failed");
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
@@ -51,23 +56,21 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     return STPDE_OK;
 }
 
-template <int KC, bool GEN, int SPEC = 0>
+template <int KC, int SPEC = 0>
 static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
                              cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
-    static unsigned long long configured = 0;   // bit per device: function attributes are per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, GEN, tc::kModeFwd, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static DeviceOnce configured;
+    if (configured.first_use()) {
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, tc::kModeFwd, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel) failed");
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = tc.num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, GEN, tc::kModeFwd, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    tc::tc_layer_pair_kernel<KC, tc::kModeFwd, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -79,18 +82,16 @@ static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CU
                                   const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     const size_t smem = (size_t)tc::kPairSmemBudget + 1024 + 512;
-    static unsigned long long configured = 0;
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
-        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, false, MODE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static DeviceOnce configured;
+    if (configured.first_use()) {
+        if (cudaFuncSetAttribute(tc::tc_layer_pair_kernel<KC, MODE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_pair_kernel, training mode) failed");
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, false, MODE, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    tc::tc_layer_pair_kernel<KC, MODE, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -101,14 +102,13 @@ static int launch_layer_mode(int num_sms, const CUtensorMap& w_hi, const CUtenso
                              const CUtensorMap& a_lo, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st) {
     constexpr int NR = tc::rows_per_tile(KC);
     constexpr int N = KC * NR;
-    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) + 1024 + 256;
-    static unsigned long long configured = 0;
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!(configured >> (dev_ & 63) & 1ull)) {
+    const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) +
+                        tc::epi_staging_total<KC, MODE>() + 1024 + 256;
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel, training mode) failed");
-        configured |= 1ull << (dev_ & 63);
+        configured.mark();
     }
     const int n_tiles = ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;

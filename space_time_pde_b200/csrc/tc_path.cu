@@ -53,25 +53,6 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
     }
 }
 
-// Tables for the fused layer-0 generator: wx0p [kp][4] (zero padded) and coef [KC][kp] with
-// coef[0] = 2^4, first order = W0x[:, dir] * 2^4, second order = W0x[:, a] * W0x[:, b] * 2^4 (0 for pad features)
-__global__ void gen_tables_kernel(JetSpec spec, int dim, int n0, int kp, const float* __restrict__ Wx0,
-                                  float* __restrict__ wx0p, float* __restrict__ coef) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= kp) return;
-    float wx[kMaxDim] = {0.f, 0.f, 0.f, 0.f};
-    const bool ok = f < n0;
-    for (int k = 0; k < dim; ++k) wx[k] = ok ? Wx0[f * dim + k] : 0.f;
-    for (int k = 0; k < kMaxDim; ++k) wx0p[f * 4 + k] = wx[k];
-    const float sc = ok ? (float)(1 << tc::kActScaleLog2) : 0.f;
-    for (int c = 0; c < spec.kc; ++c) {
-        float v = sc;
-        if (spec.kind[c] == 1) v *= wx[spec.dir[c]];
-        if (spec.kind[c] == 2) v *= wx[spec.dir[spec.pa[c]]] * wx[spec.dir[spec.pb[c]]];
-        coef[(int64_t)c * kp + f] = v;
-    }
-}
-
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
 // One thread = 4 consecutive features of one row per iteration (8-byte stores, 256 B per warp and plane); the
 // per-feature constants live in registers, the next row's operands are prefetched while the current row is
@@ -189,7 +170,6 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
 // ---------------------------------------------------------------------------------------------
 size_t tc_fixed_bytes(int n_layers, const int* widths) {
     size_t off = 1024;  // wscale + absmax
-    off += align_up((size_t)round_up(widths[0], 64) * (4 + kMaxComp) * sizeof(float), 1024);  // generator tables
     for (int l = 1; l <= n_layers - 2; ++l) {
         size_t plane = (size_t)round_up(widths[l], 128) * round_up(widths[l - 1], 64) * sizeof(__half);
         off += 2 * align_up(plane, 1024);
@@ -254,6 +234,40 @@ static int make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uin
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Process-wide switches read from the environment ONCE (getenv is not free and not thread-safe against setenv):
+// STPDE_TC_PAIR=0 disables the CTA-pair kernels, STPDE_WAIT_NS overrides the mbarrier suspend-time hint.
+const TcEnv& tc_env() {
+    static const TcEnv env = [] {
+        TcEnv e;
+        const char* p = getenv("STPDE_TC_PAIR");
+        e.use_pair = p ? atoi(p) : 1;
+        const char* w = getenv("STPDE_WAIT_NS");
+        e.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u;
+        return e;
+    }();
+    return env;
+}
+
+// TMA store maps of a layer's output planes [kc][rows][ld_out]: box = 32 features x stage_rows(kc) rows x kc components,
+// no swizzle (the epilogue warps write their staging buffers in exactly that order).
+int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32) {
+    cuuint64_t dims[3] = {(cuuint64_t)a.ld_out, (cuuint64_t)a.rows, (cuuint64_t)kc};
+    const size_t es = f32 ? sizeof(float) : sizeof(__half);
+    cuuint64_t strides[2] = {(cuuint64_t)a.ld_out * es, (cuuint64_t)a.ld_out * a.rows * es};
+    cuuint32_t box[3] = {32, (cuuint32_t)tc::stage_rows(kc), (cuuint32_t)kc};
+    cuuint32_t estr[3] = {1, 1, 1};
+    void* planes[2] = {plane0, plane1};
+    for (int i = 0; i < 2; ++i) {
+        if (!planes[i]) { a.out_map[i] = a.out_map[0]; continue; }
+        CUresult r = encode_fn()(&a.out_map[i], f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                 planes[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return tc_fail(STPDE_ECUDA, "cuTensorMapEncodeTiled failed (output planes)");
+    }
+    return STPDE_OK;
+}
+
 // helpers shared with the reverse-mode path (tc_bwd.cu)
 int tc_make_map_2d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1) {
     return make_map_2d(m, base, d0, d1, b0, b1);
@@ -279,17 +293,12 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.rows = rows;
     tc.passes = precision == STPDE_PREC_FP16X3 ? 3 : 1;
     tc.status = status;
-    const char* pair_env = getenv("STPDE_TC_PAIR");
-    tc.use_pair = pair_env ? atoi(pair_env) : 1;
-    // Fusing layer 0 into layer 1's operand producer (generator warps) is functional but measured SLOWER on B200
-    // (905 ms vs 435 + 122 ms at BASELINE config 2: the generator needs ~2000 issue slots per K block and the
-    // 4 feature-tile passes recompute it 4 times), so it is opt-in: STPDE_TC_FUSE0=1.
+    tc.use_pair = tc_env().use_pair;
+    // (Fusing layer 0 into layer 1's operand producer was tried in round 1 and measured slower - 905 ms vs 435 + 122 ms
+    // at BASELINE config 2, the 4 feature-tile passes regenerate the operand 4 times - and removed in round 2.)
     // The tensor-core kernels use the MUFU-based activation jets (act_jet_fast): measured on B200, switching to the
     // libdevice-accurate versions changes the fp16x3 error by < 2 % (the 2^-22 operand rounding dominates) and
     // costs 4 % of the step.
-    tc.fast_act = 1;
-    const char* fuse_env = getenv("STPDE_TC_FUSE0");
-    tc.fuse0 = fuse_env ? atoi(fuse_env) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -298,9 +307,6 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.absmax = (unsigned*)(fixed_ws + 512);
     cudaMemsetAsync(tc.absmax, 0, 256, st);
     size_t off = 1024;
-    tc.wx0p = (float*)(fixed_ws + off);
-    tc.coef0 = tc.wx0p + (size_t)round_up(widths[0], 64) * 4;
-    off += align_up((size_t)round_up(widths[0], 64) * (4 + kMaxComp) * sizeof(float), 1024);
     int me, mo;
     plane_lds(n_layers, widths, me, mo);
     const size_t plane_even = (size_t)kc * rows * me * sizeof(__half), plane_odd = (size_t)kc * rows * mo * sizeof(__half);
@@ -365,8 +371,7 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
                  const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
                  int np_last, cudaStream_t st) {
     if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_prepare");
-    const bool fuse0 = tc.use_pair && tc.fuse0 && tc.layer[1].n_feat >= 2 * tc::kTileF;
-    if (!fuse0) {
+    {
         ProfScope ps(kSlotLayer0, st);
         STPDE_TC_DISPATCH_KC(spec.kc, launch_layer0_tc<KC>(tc, spec, dim, act, beta, cb, tc.n0,
                                                            (const float*)(ws + off_wx[0]), Vb, ncat, st));
@@ -398,20 +403,11 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         a.status = tc.status;
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
-        a.fast_act = tc.fast_act;
-        { const char* w = getenv("STPDE_WAIT_NS"); a.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u; }
-        a.n0 = tc.n0;
-        a.wx0p = tc.wx0p;
-        a.coef0 = tc.coef0;
-        a.vb_vec = (ncat % 4 == 0) && (tc.n0 % 64 == 0);
-        if (l == 1 && fuse0 && !tc.tables_ready) {
-            gen_tables_kernel<<<(L.kp_in + 127) / 128, 128, 0, st>>>(spec, dim, tc.n0, L.kp_in,
-                                                                      (const float*)(ws + off_wx[0]), tc.wx0p, tc.coef0);
-            tc.tables_ready = 1;
-        }
-        if (l == 1 && fuse0) {
-            rc = tc_launch_layer_pair_gen(spec.kc, tc, L, spec, a, st);
-        } else if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
+        a.wait_ns = tc_env().wait_ns;
+        rc = L.last ? tc_encode_out_maps(a, spec.kc, act_last, nullptr, true)
+                    : tc_encode_out_maps(a, spec.kc, a.out_hi, tc.passes == 3 ? (void*)a.out_lo : nullptr, false);
+        if (rc) return rc;
+        if (tc.use_pair && L.n_feat >= 2 * tc::kTileF) {
             rc = tc_launch_layer_pair(spec.kc, tc, L, spec, a, st);
         } else {
             rc = tc_launch_layer(spec.kc, tc, L, spec, a, st);

@@ -4,10 +4,17 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 #include "kernels.h"
 
 namespace stpde {
+
+struct TcEnv {
+    int use_pair;
+    uint32_t wait_ns;
+};
+const TcEnv& tc_env();   // environment switches, read once per process
 
 struct TcLayerPlan {
     int n_feat, np128, kp_in, ld_out, n_store, last, cat_off;
@@ -16,8 +23,7 @@ struct TcLayerPlan {
 };
 
 struct TcContext {
-    int n_layers, kc, rows, passes, num_sms, use_pair, fuse0, tables_ready, fast_act;
-    float *wx0p, *coef0;              // fused layer-0 generator tables
+    int n_layers, kc, rows, passes, num_sms, use_pair;
     TcLayerPlan layer[kMaxLayers];     // hidden layers 1..n_layers-2
     __half* act[2][2];                 // [buffer parity][hi/lo] planes [KC][rows][ld]
     int ld0, n0;                       // row stride / true width of layer 0's output planes

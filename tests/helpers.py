@@ -70,7 +70,11 @@ def rel_err_quantile(a, b, q=0.995):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
-    return float(np.quantile(np.abs(a - b) / (den if den > 0 else 1.0), q))
+    e = np.abs(a - b) / (den if den > 0 else 1.0)
+    qv = float(np.quantile(e, q))
+    # the plain L-infinity is reported beside every quantile-gated comparison (parity report, see record())
+    record("linf_beside_quantile", os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], float(np.max(e)), qv)
+    return qv
 
 
 GRAD_CASES = ["rb2_tanh", "rb2_softplus", "rb2_elu", "rb2_swish", "rb2_paper_softplus", "rb2_nonunit_tanh",
@@ -93,3 +97,14 @@ def pde_layer_for(sp, name, case):
     for eq_name, (string, subs) in eqs.items():
         layer.add_equation(string, eq_name, subs_dict=subs)
     return layer
+
+
+def record(test, what, err, gate):
+    """Append one measured parity figure to the JSON-lines file named by STPDE_PARITY_REPORT (the GPU sessions set it;
+    the committed copy is profiles/r02_parity_report.jsonl).  Returns err so that it can sit inside an assert."""
+    path = os.environ.get("STPDE_PARITY_REPORT")
+    if path:
+        import json
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": test, "what": what, "err": float(err), "gate": float(gate)}) + "\n")
+    return err

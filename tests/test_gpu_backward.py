@@ -14,7 +14,7 @@ import torch
 import space_time_pde_b200 as sp
 from space_time_pde_b200 import _torch_jets, jets
 from space_time_pde_b200.equations import JetSpec
-from tests.helpers import GRAD_CASES, load_case, load_grads, pde_layer_for, rel_linf
+from tests.helpers import GRAD_CASES, load_case, load_grads, pde_layer_for, record, rel_linf
 from tests.test_host_logic import bounds, build_model
 
 pytestmark = pytest.mark.gpu
@@ -39,26 +39,29 @@ def make_decoder(gen, d, c, o, nf, dev):
     return Ws, bs
 
 
-def reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj):
-    g64 = grid.double().requires_grad_(True)
-    W64 = [w.double().requires_grad_(True) for w in Ws]
-    b64 = [b.double().requires_grad_(True) for b in bs]
-    beta_t = torch.tensor(beta, dtype=torch.float64, device=grid.device, requires_grad=(act == "swish"))
+def reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj, dtype=torch.float64):
+    """Autograd of the torch jets for the cotangents (gy, gj); dtype=float32 gives the plain-PyTorch-fp32 evaluation of
+    the same function, whose distance from the float64 one is the noise floor the gates are pinned to."""
+    g64 = grid.to(dtype).requires_grad_(True)
+    W64 = [w.to(dtype).requires_grad_(True) for w in Ws]
+    b64 = [b.to(dtype).requires_grad_(True) for b in bs]
+    beta_t = torch.tensor(beta, dtype=dtype, device=grid.device, requires_grad=(act == "swish"))
     grads = None
     p = q.shape[1]
     step = 512                                           # bounded autograd tape
     for s in range(0, p, step):
         sl = slice(s, min(p, s + step))
-        y, j = _torch_jets.query_jets(g64, q[:, sl].double(), lo.to(grid.device), hi.to(grid.device), W64, b64, act, beta_t, spec)
-        loss = (y * gy[:, sl].double()).sum()
+        y, j = _torch_jets.query_jets(g64, q[:, sl].to(dtype), lo.to(grid.device), hi.to(grid.device), W64, b64, act, beta_t, spec)
+        loss = (y * gy[:, sl].to(dtype)).sum()
         if j is not None:
-            loss = loss + (j * gj[:, :, sl].double()).sum()
+            loss = loss + (j * gj[:, :, sl].to(dtype)).sum()
         leaves = [g64] + W64 + b64 + ([beta_t] if act == "swish" else [])
         gs = torch.autograd.grad(loss, leaves, allow_unused=True)
         gs = [torch.zeros_like(t) if g is None else g for g, t in zip(gs, leaves)]
         grads = gs if grads is None else [a + b for a, b in zip(grads, gs)]
     n = len(Ws)
-    reference_grads.last_gbeta = float(grads[1 + 2 * n]) if act == "swish" else None
+    if dtype == torch.float64:
+        reference_grads.last_gbeta = float(grads[1 + 2 * n]) if act == "swish" else None
     return grads[0], grads[1:1 + n], grads[1 + n:1 + 2 * n]
 
 
@@ -90,6 +93,15 @@ def run_case(dev, d, gshape, c, o, nf, act, first, second, p, precision, seed=0,
         errs[f"b{l}"] = rel_linf(gB[l].cpu().numpy(), rB[l].cpu().numpy())
     print(f"bwd {act} d={d} nf={nf} K={1 + len(first) + len(second)} {precision}: " +
           " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    # noise floor: plain PyTorch float32 autograd of the same jets against the float64 one (whole tensors)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fgrid, fW, fB = reference_grads(grid, q, lo, hi, Ws, bs, act, beta, spec, gy, gj, dtype=torch.float32)
+    noise = max([rel_linf(fgrid.cpu().numpy(), rgrid.cpu().numpy())] +
+                [rel_linf(a.cpu().numpy(), b.cpu().numpy()) for a, b in zip(fW + fB, rW + rB)])
+    run_case.noise = noise
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    record(test, "max gradient error (fused CUDA sweep vs float64 autograd)", max(errs.values()), BWD_TOLS[precision])
+    record(test, "torch float32 autograd vs float64 autograd (noise floor)", noise, 0.0)
     return errs
 
 
@@ -241,8 +253,10 @@ def test_chunked_training_accumulates_like_one_batch(dev):
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_loss_backward_matches_reference_golden_gradients(name, dev):
     """PDELayer + training-style loss + loss.backward() on the GPU (fused forward, fused reverse sweep) against the
-    gradients of the REAL reference (float64, tests/golden/make_golden_grads.py).  Tolerance 1e-4 rel-L-infinity per
-    tensor: the golden losses are means, so the cotangents are ~1e-3 .. 1e-2 and exercise the adjoint rescaling."""
+    gradients of the REAL reference (float64, tests/golden/make_golden_grads.py).  Gate per tensor: rel-L-infinity
+    max(1e-5, 2 * err(reference float32, reference float64)) with the reference's own float32 noise stored in the
+    fixture (``noise_*``, measured 4e-7 .. 8e-7 on these cases, so the gate is 1e-5); the golden losses are means, so
+    the cotangents are ~1e-3 .. 1e-2 and exercise the adjoint rescaling."""
     c, g = load_case(name), load_grads(name)
     o = c["Ws"][5].shape[0]
     model = build_model(c, o).to(dev)
@@ -262,7 +276,10 @@ def test_loss_backward_matches_reference_golden_gradients(name, dev):
     if "g_beta" in g:   # learnable Swish beta (reference src/nonlinearities.py:5-13): gradient from the same fused sweep
         errs["beta"] = rel_linf(model.activ.beta.grad.cpu().numpy().reshape(1), g["g_beta"])
     print(name, " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
-    assert max(errs.values()) < 1e-4, errs
+    for k, v in errs.items():
+        key = "noise_" + ("grid" if k == "grid" else k)
+        gate = max(1e-5, 2 * float(g[key])) if key in g else 1e-5
+        assert record("golden_gradients:" + name, k, v, gate) < gate, (k, errs)
 
 
 def test_single_pass_backward_option(dev):

@@ -14,7 +14,9 @@ import space_time_pde_b200 as sp
 from oracle import jet_oracle as jo
 from space_time_pde_b200 import jets
 from space_time_pde_b200.equations import JetSpec
-from tests.helpers import rel_linf
+import os
+
+from tests.helpers import GOLDEN, record, rel_linf
 from tests.test_gpu_backward import reference_grads
 
 pytestmark = pytest.mark.gpu
@@ -35,7 +37,16 @@ def oracle_check(model, grid, q, act, spec, y, jt, n_check, tol):
     for i, ref in enumerate(planes):
         errs[f"jet{i}"] = rel_linf(jt[i][:, :n_check].cpu().numpy(), ref)
     print({k: f"{v:.1e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        record(os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], k, v, tol)
     assert max(errs.values()) < tol, errs
+
+
+def reference_noise_gate(fixture, key, cap):
+    """max(1e-5, 2 * err(reference fp32, reference fp64)) measured by the REAL reference at this configuration's shape
+    (tests/golden/make_golden_seeded.py), never looser than the round-1 figure `cap`."""
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    return min(max(1e-5, 2 * rel_linf(z[key + "_f32"], z[key + "_f64"])), cap)
 
 
 def test_config3_paper_training_shape_fp16(dev):
@@ -84,13 +95,16 @@ def test_config4_ns4d_width256_second_order(dev):
         yl, res = layer(q)
         y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), "softplus", None, spec=spec)
     assert torch.equal(yl, y) and all(torch.isfinite(v).all() for v in res.values())
-    # d = 4 blends 16 corners with 1/cubesize^2-scaled cancellations: 3e-5 on second derivatives (see test_gpu_parity)
-    oracle_check(model, grid, q, "softplus", spec, y, jt, 48, 3e-5)
+    # Gate: the reference's own float32 run is 5.8e-3 away from its float64 run on the second derivatives at exactly this
+    # configuration (fixture seeded_cfg4_ns4d_nf256, real reference), i.e. max(1e-5, 2 * noise) = 1.2e-2; the product is
+    # held to 3e-5.  (The same fixture is checked value by value in tests/test_gpu_seeded_golden.py.)
+    gate4 = reference_noise_gate("seeded_cfg4_ns4d_nf256", "g2diag", 3e-5)
+    oracle_check(model, grid, q, "softplus", spec, y, jt, 48, gate4)
     # residuals from the same jets, evaluated by numpy from the oracle's planes
     yj = jo.query_jet(grid.cpu().numpy(), q[:, :48].cpu().numpy(), 0., 1., [l.weight.detach().cpu().numpy() for l in model.fc],
                       [l.bias.detach().cpu().numpy() for l in model.fc], "softplus")
     cont = yj.g[0][..., 0] + yj.g[1][..., 1] + yj.g[2][..., 2]
-    assert rel_linf(res["continuity"][:, :48, 0].cpu().numpy(), cont) < 3e-5
+    assert record("config4", "continuity", rel_linf(res["continuity"][:, :48, 0].cpu().numpy(), cont), gate4) < gate4
 
 
 def test_config5_sweep_shape_forward_and_backward(dev):
@@ -101,8 +115,10 @@ def test_config5_sweep_shape_forward_and_backward(dev):
     spec = JetSpec((0, 1, 2), ((1, 1), (2, 2)))
     with torch.no_grad():
         y, jt = sp.fused_query(grid, q, 0., 1., list(model.fc), "softplus", None, spec=spec)
-    # cubesize = 1/31: second derivatives carry 31^2 ~ 1e3 x the rounding of the value path
-    oracle_check(model, grid, q, "softplus", spec, y, jt, 256, 2e-5)
+    # cubesize = 1/31: second derivatives carry 31^2 ~ 1e3 x the rounding of the value path.  Gate: the reference's own
+    # float32 run is 1.7e-3 away from its float64 run there (fixture seeded_cfg5_rb2_nf32_c128) -> max(1e-5, 2 * noise)
+    # = 3.4e-3; the product is held to 2e-5.
+    oracle_check(model, grid, q, "softplus", spec, y, jt, 256, reference_noise_gate("seeded_cfg5_rb2_nf32_c128", "g2diag", 2e-5))
     # reverse sweep on a subset (the float64 autograd checker keeps a tape of rows x widths)
     n = 512
     gen = torch.Generator().manual_seed(55)
