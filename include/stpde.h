@@ -20,6 +20,7 @@
  *                                 reference differentiate THROUGH every autograd.grad call): gradients w.r.t. the
  *                                 decoder weights / biases and the latent grid in one reverse sweep over the jets
  *   stpde_residuals            <- src/pde.py:139-142 (evaluation of the lambdified equations)
+ *   stpde_residual_loss        <- the same + experiments/rb2d/train.py:70-75 (l1 / l2 / huber loss reductions)
  *   stpde_jet_forward_host     <- same as stpde_jet_forward with HOST buffers (copies inside)
  *
  * Conventions
@@ -231,6 +232,35 @@ int stpde_residuals_backward(int32_t batch, int32_t npts, int32_t dim, int32_t o
                              const float *q, const int64_t *q_strides, const float *y, const float *jets,
                              const int32_t *prog, int32_t prog_words, const float *consts, int32_t n_consts,
                              int32_t n_eq, const float *gres, float *gy, float *gjets, void *stream);
+
+/*
+ * Fused residual + loss reduction - replaces, for training, the lambdified residual arithmetic of
+ * src/pde.py:139-142 TOGETHER with the loss reductions of experiments/rb2d/train.py:70-75
+ *     reg_loss = loss_func(pred_value, point_value);  pde_loss = loss_func(stack(residues), 0)
+ * loss_kind: 0 = l1 (F.l1_loss), 1 = l2 (F.mse_loss), 2 = huber (F.smooth_l1_loss, beta 1); train.py:31-39.
+ * The residuals never reach memory: every CTA writes one pair of partial SUMS
+ *     partial[block] = { sum l(y - target), sum over equations l(residual) }      (target may be NULL = zeros)
+ * for stpde_residual_loss_blocks(batch * npts) blocks; the caller adds them (mean loss = sum / count, which is also
+ * what makes one all-reduce of [sums | counts | gradients] equal the single-process means).
+ */
+int32_t stpde_residual_loss_blocks(int64_t total_points);
+int stpde_residual_loss(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                        const float *q, const int64_t *q_strides, const float *y, const float *jets,
+                        const float *target, const int32_t *prog, int32_t prog_words, const float *consts,
+                        int32_t n_consts, int32_t n_eq, int32_t loss_kind, float *partial, void *stream);
+
+/*
+ * Reverse mode of stpde_residual_loss (the part of loss.backward(), train.py:77, between the two loss scalars and the
+ * decoder outputs): g_sums = { d loss / d reg_sum, d loss / d pde_sum } (device pointer, 2 floats); the residuals are
+ * recomputed, their cotangents g_pde * l'(r_e) stay in registers and feed the adjoint programs of
+ * stpde_residuals_backward; gy additionally receives g_reg * l'(y - target).  Outputs gy [b,p,o], gjets [n_jet,b,p,o].
+ */
+int stpde_residual_loss_backward(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                                 const float *q, const int64_t *q_strides, const float *y, const float *jets,
+                                 const float *target, const int32_t *prog, int32_t prog_words, const float *consts,
+                                 int32_t n_consts, const int32_t *adj_prog, int32_t adj_words,
+                                 const float *adj_consts, int32_t n_adj_consts, int32_t n_eq, int32_t loss_kind,
+                                 const float *g_sums, float *gy, float *gjets, void *stream);
 
 /*
  * Instrumentation (bench.py): every kernel launch is counted per slot; with profiling enabled each

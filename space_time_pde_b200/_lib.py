@@ -49,7 +49,8 @@ EXPORTS = ["stpde_version", "stpde_last_error", "stpde_desc_size", "stpde_device
            "stpde_interp_coefficients", "stpde_interp", "stpde_jet_forward", "stpde_jet_forward_host",
            "stpde_backward_workspace_bytes", "stpde_backward_chunk_points", "stpde_jet_backward",
            "stpde_jet_forward_train",
-           "stpde_residuals", "stpde_residuals_backward", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
+           "stpde_residuals", "stpde_residuals_backward", "stpde_residual_loss_blocks", "stpde_residual_loss",
+           "stpde_residual_loss_backward", "stpde_profile_enable", "stpde_profile_read", "stpde_profile_slot_name"]
 
 
 class StpdeError(RuntimeError):
@@ -142,6 +143,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.stpde_residuals_backward.restype = c_int
     lib.stpde_residuals_backward.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, i32p, i32, f32p,
                                              i32, i32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.stpde_residual_loss_blocks.restype = i32
+    lib.stpde_residual_loss_blocks.argtypes = [ctypes.c_int64]
+    lib.stpde_residual_loss.restype = c_int
+    lib.stpde_residual_loss.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, c_void_p, i32p, i32, f32p,
+                                        i32, i32, i32, c_void_p, c_void_p]
+    lib.stpde_residual_loss_backward.restype = c_int
+    lib.stpde_residual_loss_backward.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, c_void_p, i32p, i32,
+                                                 f32p, i32, i32p, i32, f32p, i32, i32, i32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stpde_residuals.restype = c_int
     lib.stpde_residuals.argtypes = [i32, i32, i32, i32, i32, c_void_p, i64p, c_void_p, c_void_p, i32p, i32, f32p,
                                     i32, i32, c_void_p, c_void_p]

@@ -637,14 +637,12 @@ int stpde_jet_forward_host(const stpde_desc_t* desc, const float* grid, const fl
     return rc;
 }
 
-int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet, const float* q,
-                    const int64_t* q_strides, const float* y, const float* jets, const int32_t* prog,
-                    int32_t prog_words, const float* consts, int32_t n_consts, int32_t n_eq, float* residuals,
-                    void* stream) {
-    static thread_local ResidualProgram rp;
+// shared validation of a forward residual program (stack discipline is checked on the host so that the kernels cannot
+// run out of their 16-entry stacks)
+static int check_forward_program(const int32_t* prog, int32_t prog_words, int32_t n_consts, int32_t dim, int32_t out_features,
+                                 int32_t n_jet, int32_t n_eq) {
     if (prog_words < 0 || prog_words > 640 || (prog_words & 1)) return fail(STPDE_EUNSUPPORTED, "program too long (%d words)", prog_words);
     if (n_consts < 0 || n_consts > 128) return fail(STPDE_EUNSUPPORTED, "too many constants (%d)", n_consts);
-    // validate stack discipline on the host so the kernel cannot run out of its 16-entry stack
     int sp = 0, eq = 0;
     for (int w = 0; w < prog_words; w += 2) {
         int op = prog[w], arg = prog[w + 1];
@@ -661,6 +659,16 @@ int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_featur
         if (sp > 16) return fail(STPDE_EUNSUPPORTED, "expression too deep");
     }
     if (eq != n_eq || sp != 0) return fail(STPDE_EINVAL, "program has %d equations, expected %d", eq, n_eq);
+    return STPDE_OK;
+}
+
+int stpde_residuals(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet, const float* q,
+                    const int64_t* q_strides, const float* y, const float* jets, const int32_t* prog,
+                    int32_t prog_words, const float* consts, int32_t n_consts, int32_t n_eq, float* residuals,
+                    void* stream) {
+    static thread_local ResidualProgram rp;
+    int rc = check_forward_program(prog, prog_words, n_consts, dim, out_features, n_jet, n_eq);
+    if (rc) return rc;
     rp.n_words = prog_words;
     memcpy(rp.words, prog, prog_words * sizeof(int32_t));
     memcpy(rp.consts, consts, n_consts * sizeof(float));
@@ -706,6 +714,79 @@ int stpde_residuals_backward(int32_t batch, int32_t npts, int32_t dim, int32_t o
         ProfScope ps(kSlotResidual, (cudaStream_t)stream);
         launch_residuals_backward(rp, npts, (int64_t)batch * npts, dim, out_features, n_jet, n_eq, q, q_strides, y, jets, gres,
                                   gy, gjets, (cudaStream_t)stream);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STPDE_OK;
+}
+
+
+int32_t stpde_residual_loss_blocks(int64_t total_points) { return residual_loss_blocks(total_points); }
+
+int stpde_residual_loss(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet, const float* q,
+                        const int64_t* q_strides, const float* y, const float* jets, const float* target,
+                        const int32_t* prog, int32_t prog_words, const float* consts, int32_t n_consts, int32_t n_eq,
+                        int32_t loss_kind, float* partial, void* stream) {
+    static thread_local ResidualProgram rp;
+    if (loss_kind < 0 || loss_kind > 2) return fail(STPDE_EINVAL, "loss kind %d", loss_kind);
+    int rc = check_forward_program(prog, prog_words, n_consts, dim, out_features, n_jet, n_eq);
+    if (rc) return rc;
+    if (n_eq > 16) return fail(STPDE_EUNSUPPORTED, "the fused loss handles at most 16 equations");
+    if (!partial) return fail(STPDE_EINVAL, "null pointer argument");
+    rp.n_words = prog_words;
+    memcpy(rp.words, prog, prog_words * sizeof(int32_t));
+    memcpy(rp.consts, consts, n_consts * sizeof(float));
+    {
+        ProfScope ps(kSlotResidual, (cudaStream_t)stream);
+        launch_residual_loss(rp, npts, (int64_t)batch * npts, out_features, n_eq, loss_kind, q, q_strides, y, jets, target,
+                             partial, (cudaStream_t)stream);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STPDE_OK;
+}
+
+int stpde_residual_loss_backward(int32_t batch, int32_t npts, int32_t dim, int32_t out_features, int32_t n_jet,
+                                 const float* q, const int64_t* q_strides, const float* y, const float* jets,
+                                 const float* target, const int32_t* prog, int32_t prog_words, const float* consts,
+                                 int32_t n_consts, const int32_t* adj_prog, int32_t adj_words, const float* adj_consts,
+                                 int32_t n_adj_consts, int32_t n_eq, int32_t loss_kind, const float* g_sums, float* gy,
+                                 float* gjets, void* stream) {
+    static thread_local ResidualProgram rp;
+    static thread_local ResidualProgramBig ap;
+    if (loss_kind < 0 || loss_kind > 2) return fail(STPDE_EINVAL, "loss kind %d", loss_kind);
+    int rc = check_forward_program(prog, prog_words, n_consts, dim, out_features, n_jet, n_eq);
+    if (rc) return rc;
+    if (n_eq > 16) return fail(STPDE_EUNSUPPORTED, "the fused loss handles at most 16 equations");
+    if (adj_words < 0 || adj_words > 2048 || (adj_words & 1)) return fail(STPDE_EUNSUPPORTED, "adjoint program too long (%d words)", adj_words);
+    if (n_adj_consts < 0 || n_adj_consts > 256) return fail(STPDE_EUNSUPPORTED, "too many constants (%d)", n_adj_consts);
+    if ((int64_t)batch * npts > 0 && (!g_sums || !gy || (n_jet > 0 && !gjets))) return fail(STPDE_EINVAL, "null pointer argument");
+    const int n_out = out_features * (1 + n_jet);
+    int sp = 0, out = 0;
+    for (int w = 0; w < adj_words; w += 2) {
+        int op = adj_prog[w], arg = adj_prog[w + 1];
+        switch (op) {
+            case 0: if (arg < 0 || arg >= n_adj_consts) return fail(STPDE_EINVAL, "const index"); ++sp; break;
+            case 1: if (arg < 0 || arg >= dim) return fail(STPDE_EINVAL, "q index"); ++sp; break;
+            case 2: if (arg < 0 || arg >= out_features) return fail(STPDE_EINVAL, "y index"); ++sp; break;
+            case 3: if (arg < 0 || arg >= n_jet * out_features) return fail(STPDE_EINVAL, "jet index"); ++sp; break;
+            case 9: if (arg < 0 || arg >= n_eq) return fail(STPDE_EINVAL, "gres index"); ++sp; break;
+            case 4: case 5: if (sp < 2) return fail(STPDE_EINVAL, "stack underflow"); --sp; break;
+            case 6: case 7: if (sp < 1) return fail(STPDE_EINVAL, "stack underflow"); break;
+            case 8: if (sp != 1) return fail(STPDE_EINVAL, "adjoint program leaves %d values", sp); sp = 0; ++out; break;
+            default: return fail(STPDE_EINVAL, "opcode %d", op);
+        }
+        if (sp > 16) return fail(STPDE_EUNSUPPORTED, "expression too deep");
+    }
+    if (out != n_out || sp != 0) return fail(STPDE_EINVAL, "adjoint program has %d outputs, expected %d", out, n_out);
+    rp.n_words = prog_words;
+    memcpy(rp.words, prog, prog_words * sizeof(int32_t));
+    memcpy(rp.consts, consts, n_consts * sizeof(float));
+    ap.n_words = adj_words;
+    memcpy(ap.words, adj_prog, adj_words * sizeof(int32_t));
+    memcpy(ap.consts, adj_consts, n_adj_consts * sizeof(float));
+    {
+        ProfScope ps(kSlotResidual, (cudaStream_t)stream);
+        launch_residual_loss_backward(rp, ap, npts, (int64_t)batch * npts, out_features, n_jet, n_eq, loss_kind, q, q_strides,
+                                      y, jets, target, g_sums, gy, gjets, (cudaStream_t)stream);
     }
     CUDA_TRY(cudaGetLastError());
     return STPDE_OK;

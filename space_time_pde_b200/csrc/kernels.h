@@ -85,4 +85,13 @@ void launch_residuals(const ResidualProgram& prog, int npts, int64_t total_pts, 
                       const float* q, const int64_t* qs, const float* y, const float* jets, float* residuals,
                       cudaStream_t st);
 
+int residual_loss_blocks(int64_t total_pts);
+void launch_residual_loss(const ResidualProgram& prog, int npts, int64_t total_pts, int O, int n_eq, int loss_kind,
+                          const float* q, const int64_t* qs, const float* y, const float* jets, const float* target,
+                          float* partial, cudaStream_t st);
+void launch_residual_loss_backward(const ResidualProgram& fwd, const ResidualProgramBig& adj, int npts, int64_t total_pts,
+                                   int O, int n_jet, int n_eq, int loss_kind, const float* q, const int64_t* qs,
+                                   const float* y, const float* jets, const float* target, const float* g_sums, float* gy,
+                                   float* gjets, cudaStream_t st);
+
 }  // namespace stpde

@@ -643,6 +643,138 @@ __global__ void residual_backward_kernel(ResidualProgramBig prog, int npts, int6
 }
 
 // ----------------------------------------------------------------------------------------------
+// Fused residual + loss reduction (reference experiments/rb2d/train.py:70-75):
+//   reg = sum over (point, output) of l(y - target),   pde = sum over (equation, point) of l(residual)
+// with l = |d| (l1), d^2 (l2) or smooth-l1 with beta 1 (huber).  The residuals never reach memory: every CTA emits one
+// (reg, pde) pair of partial sums; the caller adds the <= 4736 pairs (and divides by the counts for the mean losses).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float loss_value(int kind, float d) {
+    const float a = fabsf(d);
+    return kind == 0 ? a : kind == 1 ? d * d : (a < 1.f ? 0.5f * d * d : a - 0.5f);
+}
+__device__ __forceinline__ float loss_grad(int kind, float d) {
+    const float sg = d > 0.f ? 1.f : d < 0.f ? -1.f : 0.f;            // torch: sign(0) = 0
+    return kind == 0 ? sg : kind == 1 ? 2.f * d : (fabsf(d) < 1.f ? d : sg);
+}
+
+// postfix interpreter shared by the fused-loss kernels: evaluates every equation of `prog` at point gp into res[]
+template <class Prog>
+__device__ __forceinline__ int eval_program(const Prog& prog, int b, int p, int64_t gp, int64_t total_pts, int O,
+                                            const float* __restrict__ q, int64_t qs0, int64_t qs1, int64_t qs2,
+                                            const float* __restrict__ y, const float* __restrict__ jets,
+                                            const float* cot, float* res) {
+    float st[16];
+    int sp = 0, eq = 0;
+    for (int w = 0; w < prog.n_words; w += 2) {
+        const int op = prog.words[w], arg = prog.words[w + 1];
+        switch (op) {
+            case 0: st[sp++] = prog.consts[arg]; break;
+            case 1: st[sp++] = q[b * qs0 + p * qs1 + arg * qs2]; break;
+            case 2: st[sp++] = y[gp * O + arg]; break;
+            case 3: st[sp++] = jets[((int64_t)(arg / O) * total_pts + gp) * O + (arg % O)]; break;
+            case 4: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+            case 5: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+            case 6: st[sp - 1] = -st[sp - 1]; break;
+            case 7: {
+                float base = st[sp - 1], r = 1.f;
+                int n = arg < 0 ? -arg : arg;
+                for (int t = 0; t < n; ++t) r *= base;
+                st[sp - 1] = arg < 0 ? 1.f / r : r;
+                break;
+            }
+            case 9: st[sp++] = cot[arg]; break;           // adjoint programs: cotangent of residual `arg`
+            default:  // END
+                res[eq] = st[0];
+                sp = 0; ++eq;
+                break;
+        }
+    }
+    return eq;
+}
+
+constexpr int kMaxEq = 16;
+
+__global__ void __launch_bounds__(256) residual_loss_kernel(ResidualProgram prog, int npts, int64_t total_pts, int O, int n_eq,
+                                                            int loss_kind, const float* __restrict__ q, int64_t qs0,
+                                                            int64_t qs1, int64_t qs2, const float* __restrict__ y,
+                                                            const float* __restrict__ jets,
+                                                            const float* __restrict__ target, float* __restrict__ partial) {
+    float reg = 0.f, pde = 0.f;
+    for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < total_pts;
+         gp += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(gp / npts), p = (int)(gp % npts);
+        float res[kMaxEq];
+        eval_program(prog, b, p, gp, total_pts, O, q, qs0, qs1, qs2, y, jets, nullptr, res);
+        for (int e = 0; e < n_eq; ++e) pde += loss_value(loss_kind, res[e]);
+        for (int o = 0; o < O; ++o) reg += loss_value(loss_kind, y[gp * O + o] - (target ? target[gp * O + o] : 0.f));
+    }
+    __shared__ float red[2][8];
+    for (int off = 16; off > 0; off >>= 1) {
+        reg += __shfl_xor_sync(0xffffffffu, reg, off);
+        pde += __shfl_xor_sync(0xffffffffu, pde, off);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = reg; red[1][threadIdx.x >> 5] = pde; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        partial[blockIdx.x * 2 + threadIdx.x] = t;
+    }
+}
+
+// Reverse mode of the fused loss: the residuals are recomputed, their cotangents g_pde * l'(r_e) stay in registers and
+// feed the adjoint programs (one per output symbol, as residual_backward_kernel); gy also receives g_reg * l'(y - target).
+__global__ void __launch_bounds__(256) residual_loss_backward_kernel(ResidualProgram fwd, ResidualProgramBig adj, int npts,
+                                                                     int64_t total_pts, int O, int n_jet, int n_eq, int loss_kind,
+                                                                     const float* __restrict__ q, int64_t qs0, int64_t qs1,
+                                                                     int64_t qs2, const float* __restrict__ y,
+                                                                     const float* __restrict__ jets,
+                                                                     const float* __restrict__ target,
+                                                                     const float* __restrict__ g_sums, float* __restrict__ gy,
+                                                                     float* __restrict__ gjets) {
+    const float g_reg = g_sums[0], g_pde = g_sums[1];
+    for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < total_pts;
+         gp += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(gp / npts), p = (int)(gp % npts);
+        float cot[kMaxEq];
+        eval_program(fwd, b, p, gp, total_pts, O, q, qs0, qs1, qs2, y, jets, nullptr, cot);
+        for (int e = 0; e < n_eq; ++e) cot[e] = g_pde * loss_grad(loss_kind, cot[e]);
+        // adjoint programs: output symbols y_0..y_{O-1}, then the jet entries (plane-major)
+        float st[16];
+        int sp = 0, out = 0;
+        for (int w = 0; w < adj.n_words; w += 2) {
+            const int op = adj.words[w], arg = adj.words[w + 1];
+            switch (op) {
+                case 0: st[sp++] = adj.consts[arg]; break;
+                case 1: st[sp++] = q[b * qs0 + p * qs1 + arg * qs2]; break;
+                case 2: st[sp++] = y[gp * O + arg]; break;
+                case 3: st[sp++] = jets[((int64_t)(arg / O) * total_pts + gp) * O + (arg % O)]; break;
+                case 4: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+                case 5: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+                case 6: st[sp - 1] = -st[sp - 1]; break;
+                case 7: {
+                    float base = st[sp - 1], r = 1.f;
+                    int n = arg < 0 ? -arg : arg;
+                    for (int t = 0; t < n; ++t) r *= base;
+                    st[sp - 1] = arg < 0 ? 1.f / r : r;
+                    break;
+                }
+                case 9: st[sp++] = cot[arg]; break;
+                default:
+                    if (out < O) {
+                        const float d = y[gp * O + out] - (target ? target[gp * O + out] : 0.f);
+                        gy[gp * O + out] = st[0] + g_reg * loss_grad(loss_kind, d);
+                    } else {
+                        gjets[((int64_t)((out - O) / O) * total_pts + gp) * O + ((out - O) % O)] = st[0];
+                    }
+                    sp = 0; ++out;
+                    break;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // host-side launchers
 // ----------------------------------------------------------------------------------------------
 static inline int grid_for(int64_t n, int block) {
@@ -759,6 +891,25 @@ void launch_residuals_backward(const ResidualProgramBig& prog, int npts, int64_t
     if (total_pts == 0) return;
     residual_backward_kernel<<<grid_for(total_pts, 256), 256, 0, st>>>(prog, npts, total_pts, dim, O, n_jet, n_eq, q, qs[0],
                                                                         qs[1], qs[2], y, jets, gres, gy, gjets);
+}
+
+int residual_loss_blocks(int64_t total_pts) { return grid_for(total_pts, 256); }
+
+void launch_residual_loss(const ResidualProgram& prog, int npts, int64_t total_pts, int O, int n_eq, int loss_kind,
+                          const float* q, const int64_t* qs, const float* y, const float* jets, const float* target,
+                          float* partial, cudaStream_t st) {
+    residual_loss_kernel<<<residual_loss_blocks(total_pts), 256, 0, st>>>(prog, npts, total_pts, O, n_eq, loss_kind, q, qs[0],
+                                                                          qs[1], qs[2], y, jets, target, partial);
+}
+
+void launch_residual_loss_backward(const ResidualProgram& fwd, const ResidualProgramBig& adj, int npts, int64_t total_pts,
+                                   int O, int n_jet, int n_eq, int loss_kind, const float* q, const int64_t* qs,
+                                   const float* y, const float* jets, const float* target, const float* g_sums, float* gy,
+                                   float* gjets, cudaStream_t st) {
+    if (total_pts == 0) return;
+    residual_loss_backward_kernel<<<grid_for(total_pts, 256), 256, 0, st>>>(fwd, adj, npts, total_pts, O, n_jet, n_eq, loss_kind,
+                                                                            q, qs[0], qs[1], qs[2], y, jets, target, g_sums,
+                                                                            gy, gjets);
 }
 
 void launch_residuals(const ResidualProgram& prog, int npts, int64_t total_pts, int dim, int O, int n_jet,

@@ -31,6 +31,8 @@ constexpr int kEpiWarps = 16;   // epilogue warps (4 per TMEM lane quarter, inte
 constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ residual)
+// 18 warps x 112 registers = 63 K of the 64 K register file (__launch_bounds__(576) makes ptxas stop at 96 and spill)
+constexpr int kMaxRegs = 112;
 
 // Output staging of the epilogue: every epilogue warp owns one smem buffer holding stage_rows(KC) rows x KC
 // components x 32 features of BOTH fp16 planes (or of the fp32 plane of the last hidden layer) - 128 bytes per
@@ -49,7 +51,7 @@ constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ 
 #define STPDE_EPI_SR_DIV 1      // divides the rows per staging pass
 #endif
 constexpr int kEpiBuffers = STPDE_EPI_NBUF;
-constexpr uint32_t kRowScratch = 192;   // per epilogue warp: 8 rows x (x_0..x_3) + 8 vertex indices (160 B, padded)
+constexpr uint32_t kRowScratch = 384;   // per epilogue warp: 2 slots of 8 rows x (x_0..x_3) + 8 vertex indices (160 B, padded to 192)
 __host__ __device__ constexpr int stage_rows_base(int kc) {
     return kc == 1 ? 8 : (kc == 2 || kc == 3 || kc == 6 || kc == 9) ? 4 : kc == 8 ? 1 : 2;
 }
@@ -537,91 +539,164 @@ __device__ __forceinline__ void bwd_epilogue_tile(const JetSpec& spec, const Lay
 }
 
 
-// One tile of the forward epilogue (shared by the CTA-pair and the single-CTA kernel): TMEM -> skip term + jet
-// activation -> next layer's operand planes.
-//   * thread = output feature g (TMEM lane), 8-row blocks rb = sub, sub + EPI_PQ, ... of the tile per warp;
-//   * the per-row operands of the skip term (vertex index, cell-local coordinates) are fetched by ONE coalesced
-//     load per lane and 8-row block into a 160-byte smem scratch and read back as broadcasts (they were 4-5 global
-//     loads with 64-bit address arithmetic per (row, feature));
-//   * the accumulator buffer is handed back right after the last tcgen05.wait::ld of the warp - before any math -
-//     with release semantics (no global store of this tile is outstanding at that point);
-//   * results go to the warp's smem staging buffer with immediate-offset 2-byte stores (st.shared [base + imm]: no
-//     address arithmetic per element), SR rows at a time, and leave either through cp.async.bulk.tensor (TMA) stores -
-//     the tensor map clips rows / features at the plane bounds - or (STPDE_EPI_DRAIN) through 16-byte loads / stores
-//     of the same warp.
+// Forward epilogue of one epilogue warp over ALL its tiles (shared by the CTA-pair and the single-CTA kernel):
+// TMEM -> skip term + jet activation -> next layer's operand planes.
+//   * thread = output feature g (TMEM lane); the warp's work items are the 8-row blocks rb = sub, sub + EPI_PQ, ... of
+//     every tile of its CTA, in order;
+//   * SOFTWARE PIPELINE over the items: the skip term of item n+1 (a gather of Vb[vertex] rows - the table does not fit
+//     L2 for large latent grids, so its latency is a DRAM latency) is issued before item n is computed, and the
+//     per-row operands of item n+2 (vertex index, cell-local coordinates: one coalesced load per lane) are in flight
+//     at the same time; they pass through a 2 x 160-byte smem scratch and are read back as broadcasts.  Without this
+//     every tile exposed one global-load latency to every warp (24 % of the stall samples);
+//   * the accumulator buffer is handed back right after the last tcgen05.wait::ld of the warp - before any math;
+//   * results go to the warp's smem staging buffer with immediate-offset stores (st.shared [base + imm]: no address
+//     arithmetic per element), SR rows at a time (2 SR when only the hi plane is written), and leave through
+//     cp.async.bulk.tensor (TMA) stores - the tensor map clips rows / features at the plane bounds - or, as build
+//     variants kept for comparison, through 16-byte copies by the warp (STPDE_EPI_DRAIN) / direct stores (STPDE_EPI_DIRECT).
 // OUTK: 0 = fp16 hi + lo planes (3-pass mode), 1 = fp16 hi plane only (single pass), 2 = fp32 plane (last hidden layer).
-template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class HandBack>
-__device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
-                                                  uint32_t row_addr, int f0, int r0, int quarter, int sub, int lane,
-                                                  uint32_t taddr, uint32_t tfull_addr, uint32_t tfull_parity,
-                                                  HandBack&& hand_back) {
-    constexpr int SR = stage_rows(KC);
+// tile(it, f0, r0): first feature / first row of this CTA's it-th tile, false past the end.
+// hand_back(buf): gives TMEM accumulator buffer `buf` back to the MMA issuer.
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class TileFn, class HandBack>
+__device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
+                                                  uint32_t row_addr, int quarter, int sub, int lane, uint32_t tmem_q,
+                                                  int n_cols, uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
+    constexpr int SRB = stage_rows(KC);
+    constexpr int SR = (OUTK == 1 && SRB < 8) ? 2 * SRB : SRB;     // one plane only: twice the rows fit the buffer
     constexpr int NBUF = kEpiBuffers;
     constexpr int NPASS = 8 / SR;
-    const int fw = f0 + quarter * 32;                         // first feature of this warp
-    const int g = fw + lane;
-    const bool g_ok = g < args.n_feat;
-    if (!(fw < args.n_store && sub < NRB)) {                  // warp-uniform: nothing to do in this tile
-        mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
-        hand_back();
-        return;
-    }
+    constexpr int kMyBlocks = (NRB - 1) / EPI_PQ + 1;              // upper bound of this warp's blocks per tile
+    const bool has_blocks = sub < NRB;
     const float scale = __ldg(args.wscale);
-    // pad features [n_feat, n_store) are written as zeros; fp16 planes carry a * 2^4
-    const float sm = g_ok ? (OUTK == 2 ? 1.f : (float)(1 << kActScaleLog2)) : 0.f;
     const int n_first = spec.n_first;
-    float wx[kMaxDim];
+
+    // ---- per-feature constants, reloaded when the feature tile changes ----
+    int cur_f0 = -1, g = 0;
+    bool g_ok = false, live = false;
+    float sm = 0.f, wx[kMaxDim], wxc[KC];
+    auto load_feature_constants = [&](int f0) {
+        cur_f0 = f0;
+        const int fw = f0 + quarter * 32;
+        g = fw + lane;
+        g_ok = g < args.n_feat;
+        live = fw < args.n_store && has_blocks;
+        // pad features [n_feat, n_store) are written as zeros; fp16 planes carry a * 2^4
+        sm = g_ok ? (OUTK == 2 ? 1.f : (float)(1 << kActScaleLog2)) : 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
-    float wxc[KC];                                            // constant tangent seed of first-order components
+        for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
 #pragma unroll
-    for (int c = 0; c < KC; ++c) {
-        wxc[c] = 0.f;
+        for (int c = 0; c < KC; ++c) {
+            wxc[c] = 0.f;                                           // constant tangent seed of first-order components
 #pragma unroll
-        for (int k = 0; k < kMaxDim; ++k)
-            if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
-    }
-    const float* vb_g = args.Vb + args.cat_off + (g_ok ? g : 0);
-    // Row operands of one 8-row block -> smem scratch [8 rows][x_0..x_3] + [8] vertex indices.
-    // lane -> (coordinate plane k = lane / 8, row i = lane % 8); planes >= dim are zero.
-    auto stage_rows_of = [&](int rbase) {
-        const int rr = min(rbase + (lane & 7), args.rows - 1);
-        const float xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
-        const int vv = __ldg(args.vtx + rr);
-        __syncwarp();                                           // earlier readers of the scratch are done
-        sts_f32(row_addr + (lane & 7) * 16 + (lane >> 3) * 4, xv);
-        if (lane < 8) sts_f32(row_addr + 128 + lane * 4, __int_as_float(vv));
-        __syncwarp();
+            for (int k = 0; k < kMaxDim; ++k)
+                if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+        }
     };
-    // skip connection + per-vertex latent/bias term of the 8 rows (independent loads, issued early)
-    auto skip_terms = [&](float* zs) {
+
+    // ---- item sequence: (tile it, block rb) ----
+    struct Item { int it, rb, f0, r0; bool ok; };
+    auto first_item = [&]() {
+        Item n{0, sub, 0, 0, false};
+        n.ok = tile(0, n.f0, n.r0);
+        return n;
+    };
+    auto next_item = [&](const Item& c) {
+        Item n = c;
+        if (has_blocks && c.rb + EPI_PQ < NRB) { n.rb = c.rb + EPI_PQ; return n; }
+        n.it = c.it + 1;
+        n.rb = sub;
+        n.ok = tile(n.it, n.f0, n.r0);
+        return n;
+    };
+    // row operands of an item: lane -> (coordinate plane k = lane / 8, row i = lane % 8); planes >= dim are zero
+    auto load_rows = [&](const Item& m, float& xv, int& vv) {
+        const int rr = min(m.r0 + m.rb * 8 + (lane & 7), args.rows - 1);
+        xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
+        vv = __ldg(args.vtx + rr);
+    };
+    auto store_rows = [&](int slot, float xv, int vv) {            // -> scratch [8 rows][x_0..x_3] + [8] vertex indices
+        const uint32_t a = row_addr + slot * 192;
+        sts_f32(a + (lane & 7) * 16 + (lane >> 3) * 4, xv);
+        if (lane < 8) sts_f32(a + 128 + lane * 4, __int_as_float(vv));
+    };
+    // Vb gather of an item (its rows are in scratch slot `slot`) for THIS thread's feature of that item's tile
+    auto gather_vb = [&](const Item& m, int slot, float* zraw) {
+        const int gm = m.f0 + quarter * 32 + lane;
+        const bool ok = gm < args.n_feat;
+        const float* vb = args.Vb + args.cat_off + (ok ? gm : 0);
+        const uint32_t a = row_addr + slot * 192 + 128;
         static_for<8>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            const uint4 x = lds_v4(row_addr + i * 16);
-            const int vt = (int)lds_b32(row_addr + 128 + i * 4);
-            float z = g_ok ? __ldg(vb_g + (int64_t)vt * args.ncat) : 0.f;
+            const int vt = (int)lds_b32(a + i * 4);
+            zraw[i] = ok ? __ldg(vb + (int64_t)vt * args.ncat) : 0.f;
+        });
+    };
+
+    Item cur = first_item();
+    if (!cur.ok) return;
+    if (!has_blocks) {                                            // (K >= 9: fewer 8-row blocks than warps per quarter)
+        for (int it = 0; cur.ok; ++it, cur.ok = tile(it, cur.f0, cur.r0)) {
+            mbar_wait(tfull_addr0 + (it & 1) * 8, (it >> 1) & 1, args.status, args.wait_ns);
+            hand_back(it & 1);
+        }
+        return;
+    }
+    // prologue: rows of item 0 -> slot 0, its gather; rows of item 1 -> slot 1
+    float zs[8], zn[8];
+    {
+        float xv; int vv;
+        load_rows(cur, xv, vv);
+        store_rows(0, xv, vv);
+    }
+    Item nxt = next_item(cur);
+    {
+        float xv = 0.f; int vv = 0;
+        if (nxt.ok) load_rows(nxt, xv, vv);
+        store_rows(1, xv, vv);
+    }
+    __syncwarp();
+    gather_vb(cur, 0, zn);
+    float amax = 0.f;
+    int slot = 0;                                                   // scratch slot holding the rows of `cur`
+
+    while (cur.ok) {
+        if (cur.f0 != cur_f0) load_feature_constants(cur.f0);
+        // skip connection + per-vertex latent/bias term of the 8 rows of `cur` (gather issued one item ago)
+        static_for<8>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const uint4 x = lds_v4(row_addr + slot * 192 + i * 16);
+            float z = zn[i];
             z = fmaf(wx[0], __uint_as_float(x.x), z);
             z = fmaf(wx[1], __uint_as_float(x.y), z);
             z = fmaf(wx[2], __uint_as_float(x.z), z);
             z = fmaf(wx[3], __uint_as_float(x.w), z);
             zs[i] = z;
         });
-    };
-    float zs[8];
-    stage_rows_of(r0 + sub * 8);
-    skip_terms(zs);
-    mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
-    tc_fence_after();
-    float amax = 0.f;
-#pragma unroll 1
-    for (int rb = sub; rb < NRB; rb += EPI_PQ) {
-        const int rbase = r0 + rb * 8;
+        // prefetch: gather of the next item (rows already in the other slot), row operands of the item after it
+        Item nn = nxt.ok ? next_item(nxt) : nxt;
+        float xv2 = 0.f; int vv2 = 0;
+        if (nxt.ok) {
+            gather_vb(nxt, slot ^ 1, zn);
+            if (nn.ok) load_rows(nn, xv2, vv2);
+        }
+
+        const int buf = cur.it & 1;
+        const uint32_t taddr = tmem_q + buf * n_cols;
+        const bool first_of_tile = cur.rb == sub;
+        const bool last_of_tile = !(has_blocks && cur.rb + EPI_PQ < NRB);
+        if (first_of_tile) {
+            mbar_wait(tfull_addr0 + buf * 8, (cur.it >> 1) & 1, args.status, args.wait_ns);
+            tc_fence_after();
+        }
+        if (!live) {                                              // warp-uniform: no feature of this tile is ours
+            if (last_of_tile) hand_back(buf);
+        } else {
+        const int rbase = cur.r0 + cur.rb * 8;
+        const int fw = cur.f0 + quarter * 32;
         uint32_t v[KC][8];
 #pragma unroll
-        for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + rb * (8 * KC) + c * 8, v[c]);
-        const bool more = rb + EPI_PQ < NRB;
+        for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + cur.rb * (8 * KC) + c * 8, v[c]);
         tmem_wait_ld();
-        if (!more) hand_back();                               // the accumulator values of this warp are in registers
+        if (last_of_tile) hand_back(buf);                         // the accumulator values of this warp are in registers
         dispatch_act(args.act, [&](auto act_c) {
         constexpr int kAct = decltype(act_c)::value;
         static_for<NPASS>([&](auto PS) {
@@ -672,7 +747,7 @@ __device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const Lay
                 }
             }
 #if STPDE_EPI_DIRECT
-            // (experiment) direct stores with 64-bit address arithmetic per element
+            // (build variant) direct stores with 64-bit address arithmetic per element
 #pragma unroll
             for (int ir = 0; ir < SR; ++ir) {
                 const int r = rbase + ps * SR + ir;
@@ -696,7 +771,7 @@ __device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const Lay
                 }
             }
 #else
-            constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SR * 128) : 0;
+            constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SRB * 128) : 0;
             const uint32_t sb = stg_addr + kBufOff;
 #if !STPDE_EPI_DRAIN
             // the TMA engine must have read the previous contents of this staging buffer
@@ -722,8 +797,8 @@ __device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const Lay
                 });
             }
 #if STPDE_EPI_DRAIN
-            // drain the staging buffer with 16-byte loads / stores: lane -> (staged row = lane / LPR + k * (32 / LPR),
-            // 16-byte part = lane % LPR); a staged row is one (component, row) run of 32 features
+            // (build variant) drain the staging buffer with 16-byte loads / stores: lane -> (staged row = lane / LPR +
+            // k * (32 / LPR), 16-byte part = lane % LPR); a staged row is one (component, row) run of 32 features
             __syncwarp();
             {
                 constexpr int EB = OUTK == 2 ? 4 : 2;                    // bytes per element
@@ -764,24 +839,31 @@ __device__ __forceinline__ void fwd_epilogue_body(const JetSpec& spec, const Lay
 #endif
         });
         });
-        if (more) {
-            stage_rows_of(r0 + (rb + EPI_PQ) * 8);
-            skip_terms(zs);
         }
+        // rows of the item after next -> the slot `cur` just vacated (every lane has read its x values above)
+        __syncwarp();
+        store_rows(slot, xv2, vv2);
+        __syncwarp();
+        slot ^= 1;
+        cur = nxt;
+        nxt = nn;
     }
     if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+#if !STPDE_EPI_DIRECT && !STPDE_EPI_DRAIN
+    if (lane == 0) bulk_wait0();                                    // staging must stay valid until the last store has read it
+#endif
 }
 
-template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class HandBack>
-__device__ __forceinline__ void fwd_epilogue_tile(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
-                                                  int f0, int r0, int quarter, int sub, int lane, uint32_t taddr,
-                                                  uint32_t tfull_addr, uint32_t tfull_parity, HandBack&& hand_back) {
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class TileFn, class HandBack>
+__device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
+                                             int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
+                                             uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
     if (args.last)
-        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 2>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+        fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 2>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
     else if (args.passes == 3)
-        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+        fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
     else
-        fwd_epilogue_body<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, f0, r0, quarter, sub, lane, taddr, tfull_addr, tfull_parity, hand_back);
+        fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
 }
 
 // bytes of output staging a kernel mode needs (all 16 epilogue warps); the reverse modes still store directly
@@ -791,7 +873,7 @@ __host__ __device__ constexpr uint32_t epi_staging_total() {
 }
 
 template <int KC, int SPEC = 0, int MODE = kModeFwd>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(kMaxRegs)
 tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
@@ -903,34 +985,36 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
         // Warp w may only touch TMEM lanes 32*(w%4)..+31; the warps of a quarter take the 8-row blocks in turn.
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
-        int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            const uint32_t tempty = smem_u32(&tempty_bar[buf]);
-            // TMEM hand-back: the tcgen05.ld results are in registers (tcgen05.wait::ld), ordered before the arrive
-            auto hand_back = [&]() {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty);
-            };
-            if constexpr (MODE >= kModeBwd) {
+        const uint32_t tmem_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // TMEM hand-back: the tcgen05.ld results are in registers (tcgen05.wait::ld), ordered before the arrive
+        auto hand_back = [&](int buf) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        };
+        if constexpr (MODE >= kModeBwd) {
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
                 const int tn = t + gridDim.x;
                 const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF + quarter * 32 : -1;
                 const int next_r0 = (tn / n_ftiles) * NR;
-                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, taddr,
+                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, tmem_q + buf * N,
                                                                        smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
-                hand_back();
-            } else {
-                fwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args,
-                                                                       smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
-                                                                       smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
-                                                                       f0, r0, quarter, sub, lane, taddr,
-                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, hand_back);
+                hand_back(buf);
             }
+        } else {
+            auto tile = [&](int it, int& f0, int& r0) {
+                const int t = blockIdx.x + it * gridDim.x;
+                f0 = (t % n_ftiles) * kTileF;
+                r0 = (t / n_ftiles) * NR;
+                return t < n_tiles;
+            };
+            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+                                                              smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
+                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         }
-        if (MODE < kModeBwd && lane == 0) bulk_wait0();        // staging must stay valid until the last store has read it
     }
     tc_fence_before();
     __syncthreads();
@@ -963,6 +1047,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
+}
+// arrive on a barrier of the peer CTA with the default semantics (.release at CTA scope: no device-wide drain)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -1008,7 +1096,7 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
 }
 
 template <int KC, int MODE = kModeFwd, int SPEC = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kMaxRegs)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
@@ -1130,36 +1218,43 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         // ===================== epilogue warps (both CTAs): this CTA's 128 features x all N columns =====================
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
+        const uint32_t tmem_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
-        int it = 0;
-        for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
-            const int buf = it & 1;
-            const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * N;
-            if constexpr (MODE >= kModeBwd) {
+        if constexpr (MODE >= kModeBwd) {
+            int it = 0;
+            for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
+                const int buf = it & 1;
+                const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
                 const int tn = t + n_pairs;
                 const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32 : -1;
                 const int next_r0 = (tn / n_ftiles) * NR;
-                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, taddr,
+                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, tmem_q + buf * N,
                                                                        smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
-            } else {
-                auto hand_back = [&]() {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
-                };
-                fwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args,
-                                                                       smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
-                                                                       smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
-                                                                       f0, r0, quarter, sub, lane, taddr,
-                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, hand_back);
             }
+        } else {
+            // TMEM hand-back to the leader's barrier: the tcgen05.ld results are in registers (tcgen05.wait::ld +
+            // tcgen05.fence::before_thread_sync) and the arrive carries the default .release.cta semantics - the
+            // cluster-scope release measured 20 % of this warp's stall samples (MEMBAR + ERRBAR drain every outstanding
+            // global access, including the prefetches issued on purpose just before).
+            auto hand_back = [&](int buf) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);
+            };
+            auto tile = [&](int it, int& f0, int& r0) {
+                const int t = pair_id + it * n_pairs;
+                f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF;
+                r0 = (t / n_ftiles) * NR;
+                return t < n_tiles;
+            };
+            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+                                                              smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
+                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         }
-        if (MODE < kModeBwd && lane == 0) bulk_wait0();
     }
     tc_fence_before();
     cluster_sync_all();

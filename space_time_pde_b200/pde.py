@@ -71,6 +71,70 @@ class ResidualProgramFunction(torch.autograd.Function):
         return gy, gj, None, None, None, None, None, None, None
 
 
+LOSS_KINDS = {"l1": 0, "l2": 1, "huber": 2}
+
+
+class ResidualLossFunction(torch.autograd.Function):
+    """(y, jets) -> [reg_sum, pde_sum]: the residual programs AND the loss reductions of the reference's training step
+    (experiments/rb2d/train.py:70-75) in one kernel (``stpde_residual_loss``): the ``[n_eq, b, p]`` residual tensor, its
+    ``torch.stack`` and the elementwise loss never reach memory - every CTA emits one pair of partial sums.  Backward =
+    ``stpde_residual_loss_backward`` (residuals recomputed, their cotangents kept in registers)."""
+
+    @staticmethod
+    def forward(ctx, y, jets, xq, target, n_in, n_out, n_jet, n_eq, program, adjoint, loss_kind):
+        words, consts = program
+        b, p = xq.shape[0], xq.shape[1]
+        yc = y.detach().contiguous()
+        jc = jets.detach().contiguous() if n_jet else yc
+        tc_ = target.detach().to(torch.float32).contiguous() if target is not None else None
+        lib = _lib.load()
+        n_blocks = lib.stpde_residual_loss_blocks(b * p)
+        partial = torch.empty(n_blocks, 2, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            rc = lib.stpde_residual_loss(b, p, n_in, n_out, n_jet, xq.data_ptr(), _i64(xq.stride()), yc.data_ptr(),
+                                         jc.data_ptr(), tc_.data_ptr() if tc_ is not None else None,
+                                         (ctypes.c_int32 * len(words))(*words), len(words),
+                                         (ctypes.c_float * max(1, len(consts)))(*consts), len(consts), n_eq, loss_kind,
+                                         partial.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(yc, jc, xq, tc_ if tc_ is not None else yc.new_empty(0))
+        ctx.meta = (n_in, n_out, n_jet, n_eq, program, adjoint, loss_kind, tc_ is not None)
+        return partial.double().sum(dim=0).to(torch.float32) if b * p else y.new_zeros(2)
+
+    @staticmethod
+    def backward(ctx, gsums):
+        yc, jc, xq, tc_ = ctx.saved_tensors
+        n_in, n_out, n_jet, n_eq, program, adjoint, loss_kind, has_target = ctx.meta
+        if adjoint is None:
+            raise RuntimeError("residual programs have no adjoint program (internal error: route selection)")
+        words, consts = program
+        awords, aconsts = adjoint
+        b, p = xq.shape[0], xq.shape[1]
+        g = gsums.detach().to(torch.float32).contiguous()
+        gy = torch.empty(b, p, n_out, dtype=torch.float32, device=g.device)
+        gj = torch.empty(n_jet, b, p, n_out, dtype=torch.float32, device=g.device) if n_jet else None
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            rc = lib.stpde_residual_loss_backward(
+                b, p, n_in, n_out, n_jet, xq.data_ptr(), _i64(xq.stride()), yc.data_ptr(), jc.data_ptr(),
+                tc_.data_ptr() if has_target else None, (ctypes.c_int32 * len(words))(*words), len(words),
+                (ctypes.c_float * max(1, len(consts)))(*consts), len(consts), (ctypes.c_int32 * len(awords))(*awords),
+                len(awords), (ctypes.c_float * max(1, len(aconsts)))(*aconsts), len(aconsts), n_eq, loss_kind,
+                g.data_ptr(), gy.data_ptr(), gj.data_ptr() if gj is not None else None,
+                torch.cuda.current_stream(g.device).cuda_stream)
+        _lib.check(rc)
+        return gy, gj, None, None, None, None, None, None, None, None, None
+
+
+def _loss_elementwise(kind, d):
+    if kind == "l1":
+        return d.abs()
+    if kind == "l2":
+        return d * d
+    a = d.abs()
+    return torch.where(a < 1, 0.5 * d * d, a - 0.5)
+
+
 class PDELayer(object):
     """PDE layer for querying values and computing PDE residues."""
 
@@ -208,6 +272,47 @@ class PDELayer(object):
         for key, fn in self.eqns_fn.items():
             residues.update({key: fn(*(inputs + outputs))})
         return y, residues
+
+    def loss_sums(self, x, target=None, loss_type="l1"):
+        """Training-step losses as SUMS: returns ``(y, sums, counts)`` with
+
+            sums   = [ sum l(y - target), sum over equations and points l(residue) ]      (tensor of 2, differentiable)
+            counts = (number of regression elements, number of residue elements)
+
+        so that ``sums / counts`` are exactly the two mean losses of the reference's step (experiments/rb2d/train.py:
+        70-75: ``loss_func(pred_value, point_value)`` and ``loss_func(stack(residues), 0)`` with ``loss_type`` l1 / l2 /
+        huber as in ``loss_functional``, train.py:31-39) and a multi-GPU step all-reduces ``[sums | counts | grads]``
+        once.  With the fused forward method both reductions run inside the residual kernel (no residual tensor, no
+        ``torch.stack``); any other forward method gets the same numbers from torch ops."""
+        if loss_type not in LOSS_KINDS:
+            raise ValueError("loss_type must be 'l1', 'l2' or 'huber'")
+        names = list(self.eqns_raw.keys())
+        inputs = [x[..., i:i + 1] for i in range(x.shape[-1])]
+        x_ = torch.cat(inputs, axis=-1)
+        spec, program = self._binding()
+        if spec is not None and program is not None and names:
+            with JetRequest(spec) as request:
+                y = self.eval(x_)
+            record = request.lookup(y)
+            if (record is not None and y.is_cuda and x_.dim() == 3 and y.dtype == torch.float32 and len(names) <= 16
+                    and (self._adjoint is not None or not torch.is_grad_enabled())
+                    and os.environ.get("STPDE_RESIDUALS", "kernel") != "torch"):
+                jets = record[1]
+                sums = ResidualLossFunction.apply(y, jets if jets is not None else y.new_empty(0), x_.detach(), target,
+                                                  self.n_in, self.n_out, spec.n_jet, len(names), program, self._adjoint,
+                                                  LOSS_KINDS[loss_type])
+                n_pts = y.shape[0] * y.shape[1]
+                return y, sums, (n_pts * self.n_out, n_pts * len(names))
+        y, residues = self(x, return_residue=True)
+        d = y if target is None else y - target
+        reg = _loss_elementwise(loss_type, d).sum()
+        if residues:
+            stacked = torch.stack(list(residues.values()), dim=0)
+            pde = _loss_elementwise(loss_type, stacked).sum()
+            n_pde = stacked.numel()
+        else:
+            pde, n_pde = reg.new_zeros(()), 0
+        return y, torch.stack([reg, pde]), (d.numel(), n_pde)
 
     @property
     def eqn_num(self):

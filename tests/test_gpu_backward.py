@@ -410,3 +410,46 @@ def test_backward_empty_and_tiny_batches(dev):
     assert g2.grad is not None and g2.grad.abs().max() == 0
     errs = run_case(dev, d, (3, 4, 5), c, o, nf, "softplus", *RB2, p=1, precision="fp16x3", seed=14)
     assert max(errs.values()) < BWD_TOLS["fp16x3"], errs
+
+
+@pytest.mark.parametrize("loss_type", ["l1", "l2", "huber"])
+def test_fused_loss_sums_match_the_reference_training_losses(loss_type, dev, monkeypatch):
+    """PDELayer.loss_sums (residual programs + loss reductions in one kernel) against the reference's
+    formulation of the same step (experiments/rb2d/train.py:70-75: loss_func(pred, target), loss_func(stack(residues), 0))
+    evaluated with torch ops on the SAME fused forward: sums / counts == the mean losses to 1e-6, and the gradients of
+    alpha_reg * reg + alpha_pde * pde w.r.t. the latent grid and the decoder agree."""
+    F = {"l1": torch.nn.functional.l1_loss, "l2": torch.nn.functional.mse_loss, "huber": torch.nn.functional.smooth_l1_loss}[loss_type]
+    torch.manual_seed(21)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid0 = (torch.randn(2, 4, 6, 5, 16) * 0.5).to(dev)
+    q = torch.rand(2, 3000, 3, device=dev)
+    target = torch.randn(2, 3000, 4, device=dev) * 2.0            # |y - target| on both sides of 1: both huber branches
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+
+    def run(fused):
+        grid = grid0.clone().requires_grad_(True)
+        model.zero_grad()
+        layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+        if fused:
+            y, sums, counts = layer.loss_sums(q, target, loss_type)
+            reg, pde = sums[0] / counts[0], sums[1] / counts[1]
+        else:
+            y, res = layer(q, return_residue=True)
+            reg = F(y, target)
+            stacked = torch.stack([d for d in res.values()], dim=0)
+            pde = F(stacked, torch.zeros_like(stacked))
+        (1.0 * reg + 0.0125 * pde).backward()
+        return float(reg), float(pde), [grid.grad.clone()] + [p.grad.clone() for p in model.parameters()]
+
+    reg_f, pde_f, g_f = run(True)
+    reg_t, pde_t, g_t = run(False)
+    assert abs(reg_f - reg_t) < 1e-6 * abs(reg_t) and abs(pde_f - pde_t) < 1e-6 * abs(pde_t)
+    for a, b in zip(g_f, g_t):
+        assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    # no target (zeros) and no-grad evaluation
+    with torch.no_grad():
+        y, sums, counts = layer.loss_sums(q, None, loss_type)
+        y2, res = layer(q)
+        st = torch.stack(list(res.values()))
+        assert abs(float(sums[1] / counts[1]) - float(F(st, torch.zeros_like(st)))) < 1e-6 * float(F(st, torch.zeros_like(st)))
+        assert abs(float(sums[0] / counts[0]) - float(F(y2, torch.zeros_like(y2)))) < 1e-6 * float(F(y2, torch.zeros_like(y2)))
