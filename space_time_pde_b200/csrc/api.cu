@@ -260,14 +260,27 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
         if (rc) return fail(rc, "%s", tc_last_error());
     }
 
+    bool fused_final = false;
     for (int64_t p0 = 0; p0 < P.total_pts; p0 += pc) {
         {
             ProfScope ps(kSlotPrep, st);
             launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
         }
+        const int L = P.n_layers - 1;
         if (use_tc) {
+            // last linear layer + corner blend inside the last hidden layer's epilogue when the shape allows it
+            TcFinal fin;
+            fin.w_last = (const float*)(ws + P.off_wh[L]);
+            fin.b_last = B[L];
+            fin.n_out = P.O;
+            fin.ldw = P.kp[L];
+            fin.y = y;
+            fin.jets = jets;
+            fin.p0 = p0;
+            fin.total_pts = P.total_pts;
+            fused_final = tc_can_fuse_final(tc, P.spec, dim, P.O);
             int rc = tc_run_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, ws, P.off_wx,
-                                  act[(P.n_layers - 2) & 1], P.np[P.n_layers - 2], st);
+                                  act[(P.n_layers - 2) & 1], P.np[P.n_layers - 2], fused_final ? &fin : nullptr, st);
             if (rc) return fail(rc, "%s", tc_last_error());
         } else {
             {
@@ -283,10 +296,11 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
                                   act[l & 1], st);
             }
         }
-        const int L = P.n_layers - 1;
-        ProfScope ps(kSlotFinal, st);
-        launch_final_blend(P.spec, dim, cb.rows, cb.pc, P.total_pts, p0, P.kp[L], P.O, act[(L - 1) & 1],
-                           (const float*)(ws + P.off_wh[L]), B[L], cb, y, jets, st);
+        if (!fused_final) {
+            ProfScope ps(kSlotFinal, st);
+            launch_final_blend(P.spec, dim, cb.rows, cb.pc, P.total_pts, p0, P.kp[L], P.O, act[(L - 1) & 1],
+                               (const float*)(ws + P.off_wh[L]), B[L], cb, y, jets, st);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return STPDE_OK;

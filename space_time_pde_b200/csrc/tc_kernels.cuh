@@ -26,32 +26,30 @@ namespace tc {
 
 constexpr int kBlockK = 64;     // fp16 elements per K block = 128 B = one swizzle-128B span
 constexpr int kTileF = 128;     // features per CTA tile (UMMA M)
-constexpr int kStages = 2;      // smem ring depth (single-CTA version; the CTA-pair version fits 3-4)
+constexpr int kStages = 2;      // smem ring depth of the single-CTA kernel in the 3-pass mode (hi + lo planes per stage)
+constexpr int kSingleMaxStages = 4;   // ... and in the single-pass mode (hi planes only: half the bytes per stage)
 constexpr int kEpiWarps = 16;   // epilogue warps (4 per TMEM lane quarter, interleaved over the 8-row blocks)
 constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then epilogue
 constexpr int kActScaleLog2 = 4;  // activations are stored as fp16(a * 2^4) (+ residual)
-// 18 warps x 112 registers = 63 K of the 64 K register file (__launch_bounds__(576) makes ptxas stop at 96 and spill)
-constexpr int kMaxRegs = 112;
+// Register budget: 18 warps = 5 warps on two of the four SM sub-partitions (16 K registers each) -> 96 registers per
+// thread is the hardware limit of this block size (112 compiles but cannot launch: "too many resources").
 
 // Output staging of the epilogue: every epilogue warp owns one smem buffer holding stage_rows(KC) rows x KC
 // components x 32 features of BOTH fp16 planes (or of the fp32 plane of the last hidden layer) - 128 bytes per
 // (row, component) - which leaves the SM through one cp.async.bulk.tensor store per plane.  Sized so that the
 // operand ring of the single-CTA kernel (2 stages) and the staging of its 16 epilogue warps fit 227 KB.
-#ifndef STPDE_EPI_DIRECT
-#define STPDE_EPI_DIRECT 0      // 1: the forward epilogue stores straight to global memory (no staging, no TMA store)
-#endif
-#ifndef STPDE_EPI_DRAIN
-#define STPDE_EPI_DRAIN 0       // 1: the staging buffer is drained by the warp itself (LDS.128 + STG.128), no TMA store
-#endif
 #ifndef STPDE_EPI_NBUF
-#define STPDE_EPI_NBUF 1        // staging buffers per epilogue warp (2: a pass only waits for the store two passes back)
+#define STPDE_EPI_NBUF 1        // staging buffers per epilogue warp (2 half-size buffers measured the same as 1)
 #endif
 #ifndef STPDE_EPI_SR_DIV
-#define STPDE_EPI_SR_DIV 1      // divides the rows per staging pass
+#define STPDE_EPI_SR_DIV 1      // divides the rows per staging pass (with STPDE_EPI_NBUF=2)
 #endif
 constexpr int kEpiBuffers = STPDE_EPI_NBUF;
 constexpr uint32_t kRowScratch = 384;   // per epilogue warp: 2 slots of 8 rows x (x_0..x_3) + 8 vertex indices (160 B, padded to 192)
+// single-CTA kernel (may fuse the final layer + blend): 2 slots of 384 B (+ blend factors, corner weights) + 2 x 96 B of
+// per-point partial outputs exchanged between the four quarter-warps
+constexpr uint32_t kRowScratchFused = 1024;
 __host__ __device__ constexpr int stage_rows_base(int kc) {
     return kc == 1 ? 8 : (kc == 2 || kc == 3 || kc == 6 || kc == 9) ? 4 : kc == 8 ? 1 : 2;
 }
@@ -59,7 +57,7 @@ __host__ __device__ constexpr int stage_rows(int kc) {
     return stage_rows_base(kc) / STPDE_EPI_SR_DIV > 0 ? stage_rows_base(kc) / STPDE_EPI_SR_DIV : 1;
 }
 __host__ __device__ constexpr uint32_t epi_stage_bytes(int kc) {
-    return STPDE_EPI_DIRECT ? 0u : (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;
+    return (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;
 }
 
 // rows (point, corner) per tile for KC jet components: NR % 16 == 0 and KC * NR <= 256
@@ -184,6 +182,9 @@ template <int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
     static_for_impl(f, std::make_integer_sequence<int, N>{});
 }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA store / UMMA)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -223,6 +224,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 __device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* v) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8, "columns per load");
+    if constexpr (N == 8) tmem_ld_x8(taddr, v);
+    else if constexpr (N == 4) tmem_ld_x4(taddr, v);
+    else if constexpr (N == 2) tmem_ld_x2(taddr, v);
+    else tmem_ld_x1(taddr, v);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -272,6 +284,19 @@ struct LayerArgs {
     int g_wx_ld;
     float* g_beta;         // MODE 2/3: adjoint of the Swish beta (atomics), may be null
     uint32_t wait_ns;      // suspend-time hint of the mbarrier waits (pair kernel)
+    // ---- last hidden layer of an inference call with the final linear layer + multilinear blend fused in (OUTK 3) ----
+    int fuse_final;        // 1: this launch writes y / jets itself (no fp32 plane, no final_blend launch)
+    int n_out;             // output features O (<= 4)
+    int ldw_last;          // row stride of w_last
+    int pc;                // points in the chunk
+    long long p0, total_pts;   // first point of the chunk, points of the call
+    const float* w_last;   // [O][ldw_last] last linear layer (padded rows)
+    const float* b_last;   // [O]
+    const float* wfac;     // [d][2][pc] blend factors, dfac [d][2][pc] their derivatives, dxr [d][pc] (ChunkBuffers)
+    const float* dfac;
+    const float* dxr;
+    float* y;              // [total_pts][O]
+    float* jets;           // [n_jet][total_pts][O]
     // TMA store maps of the output planes (dims (ld_out, rows, KC), box 32 features x stage_rows(KC) rows x KC):
     // [0] = fp16 hi plane, or the fp32 plane of the last hidden layer; [1] = fp16 lo plane (3-pass mode only)
     CUtensorMap out_map[2];
@@ -551,8 +576,8 @@ __device__ __forceinline__ void bwd_epilogue_tile(const JetSpec& spec, const Lay
 //   * the accumulator buffer is handed back right after the last tcgen05.wait::ld of the warp - before any math;
 //   * results go to the warp's smem staging buffer with immediate-offset stores (st.shared [base + imm]: no address
 //     arithmetic per element), SR rows at a time (2 SR when only the hi plane is written), and leave through
-//     cp.async.bulk.tensor (TMA) stores - the tensor map clips rows / features at the plane bounds - or, as build
-//     variants kept for comparison, through 16-byte copies by the warp (STPDE_EPI_DRAIN) / direct stores (STPDE_EPI_DIRECT).
+//     cp.async.bulk.tensor (TMA) stores; the tensor map clips rows / features at the plane bounds.  (Measured against
+//     two alternatives in round 2 - the warp draining its buffer with 16-byte copies, and direct stores: within 3 %.)
 // OUTK: 0 = fp16 hi + lo planes (3-pass mode), 1 = fp16 hi plane only (single pass), 2 = fp32 plane (last hidden layer).
 // tile(it, f0, r0): first feature / first row of this CTA's it-th tile, false past the end.
 // hand_back(buf): gives TMEM accumulator buffer `buf` back to the MMA issuer.
@@ -560,6 +585,9 @@ template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class TileF
 __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
                                                   uint32_t row_addr, int quarter, int sub, int lane, uint32_t tmem_q,
                                                   int n_cols, uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
+    // scratch slot of one item: [0,128) x rows, [128,160) vertex indices, fused final only: [160,224) the point's blend
+    // factors, [224,352) corner weights [8][w, dw/dq0, dw/dq1, dw/dq2]
+    constexpr uint32_t kSlot = OUTK == 3 ? 384 : 192;
     constexpr int SRB = stage_rows(KC);
     constexpr int SR = (OUTK == 1 && SRB < 8) ? 2 * SRB : SRB;     // one plane only: twice the rows fit the buffer
     constexpr int NBUF = kEpiBuffers;
@@ -570,25 +598,33 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
     const int n_first = spec.n_first;
 
     // ---- per-feature constants, reloaded when the feature tile changes ----
+    float w5[4] = {0.f, 0.f, 0.f, 0.f};                              // fused final layer: this feature's column of W_last
     int cur_f0 = -1, g = 0;
     bool g_ok = false, live = false;
-    float sm = 0.f, wx[kMaxDim], wxc[KC];
+    constexpr bool kRb2 = SPEC == kSpecRb2 && KC == 6;               // first-order components 1..3 <-> directions 0..2
+    float sm = 0.f, wx[kMaxDim], wxc[kRb2 ? 1 : KC];                // wxc: constant tangent seed of first-order components
     auto load_feature_constants = [&](int f0) {
         cur_f0 = f0;
         const int fw = f0 + quarter * 32;
         g = fw + lane;
         g_ok = g < args.n_feat;
-        live = fw < args.n_store && has_blocks;
+        live = fw < (OUTK == 3 ? args.n_feat : args.n_store) && has_blocks;
+        if constexpr (OUTK == 3) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) w5[o] = (g_ok && o < args.n_out) ? __ldg(args.w_last + o * args.ldw_last + g) : 0.f;
+        }
         // pad features [n_feat, n_store) are written as zeros; fp16 planes carry a * 2^4
-        sm = g_ok ? (OUTK == 2 ? 1.f : (float)(1 << kActScaleLog2)) : 0.f;
+        sm = g_ok ? (OUTK >= 2 ? 1.f : (float)(1 << kActScaleLog2)) : 0.f;
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+        if constexpr (!kRb2) {
 #pragma unroll
-        for (int c = 0; c < KC; ++c) {
-            wxc[c] = 0.f;                                           // constant tangent seed of first-order components
+            for (int c = 0; c < KC; ++c) {
+                wxc[c] = 0.f;
 #pragma unroll
-            for (int k = 0; k < kMaxDim; ++k)
-                if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+                for (int k = 0; k < kMaxDim; ++k)
+                    if (spec.kind[c] == 1 && spec.dir[c] == k) wxc[c] = wx[k];
+            }
         }
     };
 
@@ -608,22 +644,30 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         return n;
     };
     // row operands of an item: lane -> (coordinate plane k = lane / 8, row i = lane % 8); planes >= dim are zero
-    auto load_rows = [&](const Item& m, float& xv, int& vv) {
+    auto load_rows = [&](const Item& m, float& xv, int& vv, float& pf) {
         const int rr = min(m.r0 + m.rb * 8 + (lane & 7), args.rows - 1);
         xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
         vv = __ldg(args.vtx + rr);
+        if constexpr (OUTK == 3) {        // blend factors of the item's point: lanes 0..5 wfac, 6..11 dfac, 12..14 dxr
+            const int ip = min((m.r0 + m.rb * 8) >> 3, args.pc - 1);
+            const float* src = lane < 6 ? args.wfac + (int64_t)lane * args.pc
+                             : lane < 12 ? args.dfac + (int64_t)(lane - 6) * args.pc
+                                         : args.dxr + (int64_t)(lane - 12) * args.pc;
+            pf = lane < 15 ? __ldg(src + ip) : 0.f;
+        }
     };
-    auto store_rows = [&](int slot, float xv, int vv) {            // -> scratch [8 rows][x_0..x_3] + [8] vertex indices
-        const uint32_t a = row_addr + slot * 192;
+    auto store_rows = [&](int slot, float xv, int vv, float pf) {  // -> scratch [8 rows][x_0..x_3] + [8] vertex indices
+        const uint32_t a = row_addr + slot * kSlot;
         sts_f32(a + (lane & 7) * 16 + (lane >> 3) * 4, xv);
         if (lane < 8) sts_f32(a + 128 + lane * 4, __int_as_float(vv));
+        if constexpr (OUTK == 3) { if (lane < 16) sts_f32(a + 160 + lane * 4, pf); }
     };
     // Vb gather of an item (its rows are in scratch slot `slot`) for THIS thread's feature of that item's tile
     auto gather_vb = [&](const Item& m, int slot, float* zraw) {
         const int gm = m.f0 + quarter * 32 + lane;
         const bool ok = gm < args.n_feat;
         const float* vb = args.Vb + args.cat_off + (ok ? gm : 0);
-        const uint32_t a = row_addr + slot * 192 + 128;
+        const uint32_t a = row_addr + slot * kSlot + 128;
         static_for<8>([&](auto I) {
             constexpr int i = decltype(I)::value;
             const int vt = (int)lds_b32(a + i * 4);
@@ -643,27 +687,28 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
     // prologue: rows of item 0 -> slot 0, its gather; rows of item 1 -> slot 1
     float zs[8], zn[8];
     {
-        float xv; int vv;
-        load_rows(cur, xv, vv);
-        store_rows(0, xv, vv);
+        float xv, pf = 0.f; int vv;
+        load_rows(cur, xv, vv, pf);
+        store_rows(0, xv, vv, pf);
     }
     Item nxt = next_item(cur);
     {
-        float xv = 0.f; int vv = 0;
-        if (nxt.ok) load_rows(nxt, xv, vv);
-        store_rows(1, xv, vv);
+        float xv = 0.f, pf = 0.f; int vv = 0;
+        if (nxt.ok) load_rows(nxt, xv, vv, pf);
+        store_rows(1, xv, vv, pf);
     }
     __syncwarp();
     gather_vb(cur, 0, zn);
     float amax = 0.f;
     int slot = 0;                                                   // scratch slot holding the rows of `cur`
+    int n_items = 0;
 
     while (cur.ok) {
         if (cur.f0 != cur_f0) load_feature_constants(cur.f0);
         // skip connection + per-vertex latent/bias term of the 8 rows of `cur` (gather issued one item ago)
         static_for<8>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            const uint4 x = lds_v4(row_addr + slot * 192 + i * 16);
+            const uint4 x = lds_v4(row_addr + slot * kSlot + i * 16);
             float z = zn[i];
             z = fmaf(wx[0], __uint_as_float(x.x), z);
             z = fmaf(wx[1], __uint_as_float(x.y), z);
@@ -672,11 +717,11 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
             zs[i] = z;
         });
         // prefetch: gather of the next item (rows already in the other slot), row operands of the item after it
-        Item nn = nxt.ok ? next_item(nxt) : nxt;
-        float xv2 = 0.f; int vv2 = 0;
+        float xv2 = 0.f, pf2 = 0.f; int vv2 = 0;
         if (nxt.ok) {
             gather_vb(nxt, slot ^ 1, zn);
-            if (nn.ok) load_rows(nn, xv2, vv2);
+            const Item nn = next_item(nxt);
+            if (nn.ok) load_rows(nn, xv2, vv2, pf2);
         }
 
         const int buf = cur.it & 1;
@@ -692,98 +737,113 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         } else {
         const int rbase = cur.r0 + cur.rb * 8;
         const int fw = cur.f0 + quarter * 32;
-        uint32_t v[KC][8];
+        // fused final layer (OUTK 3): blend accumulators of this feature over the 8 corners of the item's point
+        //   acc[0] = sum w a_0            acc[1..3] = sum dw/dq_k a_0      acc[4..6] = sum w a_{1+k}
+        //   acc[7], acc[8] = sum dw/dq_1 a_2, sum dw/dq_2 a_3           acc[9], acc[10] = sum w a_4, sum w a_5
+        // and the (lane-uniform) sums of the corner weights sw[0] = sum w, sw[1..3] = sum dw/dq_k for the bias terms
+        float acc[11], sw[4];
+        if constexpr (OUTK == 3) {
 #pragma unroll
-        for (int c = 0; c < KC; ++c) tmem_ld_x8(taddr + cur.rb * (8 * KC) + c * 8, v[c]);
-        tmem_wait_ld();
-        if (last_of_tile) hand_back(buf);                         // the accumulator values of this warp are in registers
+            for (int e = 0; e < 11; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sw[e] = 0.f;
+            // corner weights of the point: lane -> (corner j = lane % 8, which = lane / 8: 0 weight, 1 + k d/dq_k)
+            const uint32_t pa = row_addr + slot * kSlot + 160;
+            const int j = lane & 7, which = lane >> 3;
+            float wgt = 1.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx = k * 2 + ((j >> (2 - k)) & 1);
+                const float fk = __uint_as_float(lds_b32(pa + (which == k + 1 ? 24 : 0) + idx * 4));
+                wgt = k == 0 ? fk : __fmul_rn(wgt, fk);           // torch.prod order
+            }
+            sts_f32(row_addr + slot * kSlot + 224 + (j * 4 + which) * 4, wgt);
+            __syncwarp();
+        }
         dispatch_act(args.act, [&](auto act_c) {
         constexpr int kAct = decltype(act_c)::value;
         static_for<NPASS>([&](auto PS) {
             constexpr int ps = decltype(PS)::value;
-            float o[SR][KC];
+            constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SRB * 128) : 0;
+            const uint32_t sl = stg_addr + kBufOff + lane * (OUTK == 2 ? 4 : 2);
+            // TL rows at a time leave TMEM (a whole 8-row block in registers does not fit the 96-register budget next to
+            // the prefetched skip terms: spilling those made the spill store wait for the very load it was hiding)
+            constexpr int TL = SR < 4 ? SR : 4;
+            static_for<SR / TL>([&](auto CH) {
+                constexpr int ch = decltype(CH)::value;
+                uint32_t v[KC][TL];                            // row i of component c sits in accumulator column c * 8 + i
 #pragma unroll
-            for (int ir = 0; ir < SR; ++ir) {
-                const int i = ps * SR + ir;
-                float zt[KC];
-#pragma unroll
-                for (int c = 0; c < KC; ++c) zt[c] = fmaf(__uint_as_float(v[c][i]), scale, wxc[c]);
-                const float z0 = zt[0] + zs[i];
-                float s0, s1, s2;
-                act_jet_fast(kAct, args.beta, z0, s0, s1, s2);
-                if constexpr (MODE == kModeFwdSave) {
-                    const int r = rbase + i;
-                    if (g_ok && r < args.rows) {               // pre-activations for the reverse sweep
-                        const int64_t zplane = (int64_t)args.rows * args.ldz;
-                        float* pz = args.z_out + (int64_t)r * args.ldz + g;
-                        *pz = z0;
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
-                    }
-                }
-                s0 *= sm; s1 *= sm; s2 *= sm;
-                o[ir][0] = s0;
-                if constexpr (SPEC == kSpecRb2 && KC == 6) {
-                    o[ir][1] = s1 * zt[1]; o[ir][2] = s1 * zt[2]; o[ir][3] = s1 * zt[3];
-                    o[ir][4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
-                    o[ir][5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
-                } else {
-#pragma unroll
-                    for (int c = 1; c < KC; ++c) {
-                        float oc = s1 * zt[c];
-                        if (c > n_first) {                   // second order (warp-uniform): parents za, zb
-                            float za = 0.f, zb = 0.f;
-#pragma unroll
-                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                if (1 + k < KC) {
-                                    za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
-                                    zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
-                                }
-                            }
-                            oc = fmaf(s2 * za, zb, oc);
-                        }
-                        o[ir][c] = oc;
-                    }
-                }
-            }
-#if STPDE_EPI_DIRECT
-            // (build variant) direct stores with 64-bit address arithmetic per element
-#pragma unroll
-            for (int ir = 0; ir < SR; ++ir) {
-                const int r = rbase + ps * SR + ir;
-                if (r < args.rows && g < args.n_store) {
-                    const size_t off = ((size_t)r * args.ld_out + g) * (OUTK == 2 ? 4u : 2u);
-                    const size_t plane_b = (size_t)args.rows * args.ld_out * (OUTK == 2 ? 4 : 2);
+                for (int c = 0; c < KC; ++c) tmem_ld_n<TL>(taddr + cur.rb * (8 * KC) + c * 8 + ps * SR + ch * TL, v[c]);
+                tmem_wait_ld();
+                if (ps == NPASS - 1 && ch == SR / TL - 1 && last_of_tile) hand_back(buf);   // all values are in registers
+                static_for<TL>([&](auto IT) {
+                    constexpr int it_ = decltype(IT)::value;
+                    constexpr int ir = ch * TL + it_;          // row inside the staging pass
+                    constexpr int i = ps * SR + ir;            // row inside the 8-row block
+                    float zt[KC], o[KC];
 #pragma unroll
                     for (int c = 0; c < KC; ++c) {
-                        const float xs = o[ir][c];
-                        if constexpr (OUTK == 2) {
-                            *reinterpret_cast<float*>(reinterpret_cast<char*>(args.out_f32) + c * plane_b + off) = xs;
-                        } else {
-                            amax = fmaxf(amax, fabsf(xs));
-                            const __half hi = __float2half_rn(xs);
-                            *reinterpret_cast<__half*>(reinterpret_cast<char*>(args.out_hi) + c * plane_b + off) = hi;
-                            if constexpr (OUTK == 0)
-                                *reinterpret_cast<__half*>(reinterpret_cast<char*>(args.out_lo) + c * plane_b + off) =
-                                    __float2half_rn(xs - __half2float(hi));
+                        float seed;
+                        if constexpr (kRb2) seed = (c >= 1 && c <= 3) ? wx[c - 1] : 0.f;
+                        else seed = wxc[c];
+                        zt[c] = fmaf(__uint_as_float(v[c][it_]), scale, seed);
+                    }
+                    const float z0 = zt[0] + zs[i];
+                    float s0, s1, s2;
+                    act_jet_fast(kAct, args.beta, z0, s0, s1, s2);
+                    if constexpr (MODE == kModeFwdSave) {
+                        const int r = rbase + i;
+                        if (g_ok && r < args.rows) {           // pre-activations for the reverse sweep
+                            const int64_t zplane = (int64_t)args.rows * args.ldz;
+                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
+                            *pz = z0;
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
                         }
                     }
-                }
-            }
-#else
-            constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SRB * 128) : 0;
-            const uint32_t sb = stg_addr + kBufOff;
-#if !STPDE_EPI_DRAIN
-            // the TMA engine must have read the previous contents of this staging buffer
-            if (lane == 0) { if constexpr (NBUF > 1) bulk_wait_read1(); else bulk_wait_read0(); }
-            __syncwarp();
-#endif
-            {
-                const uint32_t sl = sb + lane * (OUTK == 2 ? 4 : 2);
-                static_for<SR>([&](auto IR) {
+                    s0 *= sm; s1 *= sm; s2 *= sm;
+                    o[0] = s0;
+                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                        o[1] = s1 * zt[1]; o[2] = s1 * zt[2]; o[3] = s1 * zt[3];
+                        o[4] = fmaf(s2 * zt[2], zt[2], s1 * zt[4]);
+                        o[5] = fmaf(s2 * zt[3], zt[3], s1 * zt[5]);
+                    } else {
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) {
+                            float oc = s1 * zt[c];
+                            if (c > n_first) {               // second order (warp-uniform): parents za, zb
+                                float za = 0.f, zb = 0.f;
+#pragma unroll
+                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                    if (1 + k < KC) {
+                                        za = fmaf(spec.sel_a[c][k], zt[1 + k], za);
+                                        zb = fmaf(spec.sel_b[c][k], zt[1 + k], zb);
+                                    }
+                                }
+                                oc = fmaf(s2 * za, zb, oc);
+                            }
+                            o[c] = oc;
+                        }
+                    }
+                    if constexpr (OUTK == 3) {
+                        const uint4 cw = lds_v4(row_addr + slot * kSlot + 224 + i * 16);
+                        const float w = __uint_as_float(cw.x), d0 = __uint_as_float(cw.y), d1 = __uint_as_float(cw.z),
+                                    d2 = __uint_as_float(cw.w);
+                        sw[0] += w; sw[1] += d0; sw[2] += d1; sw[3] += d2;
+                        acc[0] = fmaf(w, o[0], acc[0]);
+                        acc[1] = fmaf(d0, o[0], acc[1]); acc[2] = fmaf(d1, o[0], acc[2]); acc[3] = fmaf(d2, o[0], acc[3]);
+                        acc[4] = fmaf(w, o[1], acc[4]); acc[5] = fmaf(w, o[2], acc[5]); acc[6] = fmaf(w, o[3], acc[6]);
+                        acc[7] = fmaf(d1, o[2], acc[7]); acc[8] = fmaf(d2, o[3], acc[8]);
+                        acc[9] = fmaf(w, o[4], acc[9]); acc[10] = fmaf(w, o[5], acc[10]);
+                    } else {
+                    if constexpr (ir == 0) {
+                        // the TMA engine must have read the buffer's previous contents (a tile ago when the block is one pass)
+                        if (lane == 0) { if constexpr (NBUF > 1) bulk_wait_read1(); else bulk_wait_read0(); }
+                        __syncwarp();
+                    }
                     static_for<KC>([&](auto C) {
-                        constexpr int ir = decltype(IR)::value, c = decltype(C)::value;
-                        const float xs = o[ir][c];
+                        constexpr int c = decltype(C)::value;
+                        const float xs = o[c];
                         if constexpr (OUTK == 2) {
                             sts_f32_o<(c * SR + ir) * 128>(sl, xs);
                         } else {
@@ -794,70 +854,95 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                                 sts_b16_o<(KC * SR + c * SR + ir) * 64>(sl, __float2half_rn(xs - __half2float(hi)));
                         }
                     });
+                    }
                 });
-            }
-#if STPDE_EPI_DRAIN
-            // (build variant) drain the staging buffer with 16-byte loads / stores: lane -> (staged row = lane / LPR +
-            // k * (32 / LPR), 16-byte part = lane % LPR); a staged row is one (component, row) run of 32 features
-            __syncwarp();
-            {
-                constexpr int EB = OUTK == 2 ? 4 : 2;                    // bytes per element
-                constexpr int LPR = 32 * EB / 16;                       // lanes per staged row (4 or 8)
-                constexpr int RPI = 32 / LPR;                           // staged rows per warp instruction
-                constexpr int NPL = OUTK == 0 ? 2 : 1;                  // planes
-                const int part = lane % LPR;
-                const bool f_in = fw + part * (16 / EB) < args.n_store;
-                const size_t plane_b = (size_t)args.rows * args.ld_out * EB;
-                const uint32_t sl = sb + (lane / LPR) * (32 * EB) + part * 16;
-#pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) {
-                    char* gbase = (OUTK == 2 ? reinterpret_cast<char*>(args.out_f32)
-                                             : reinterpret_cast<char*>(pl ? args.out_lo : args.out_hi)) +
-                                  ((size_t)fw * EB + part * 16);
-                    static_for<(KC * SR + RPI - 1) / RPI>([&](auto K) {
-                        constexpr int k = decltype(K)::value;
-                        const int srow = lane / LPR + k * RPI;          // staged row: c * SR + ir
-                        const int c = srow / SR, ir = srow % SR;
-                        const int r = rbase + ps * SR + ir;
-                        if (srow < KC * SR && r < args.rows && f_in) {
-                            const uint4 val = pl ? lds_v4_o<KC * SR * 64 + k * RPI * 32 * EB>(sl) : lds_v4_o<k * RPI * 32 * EB>(sl);
-                            *reinterpret_cast<uint4*>(gbase + c * plane_b + (size_t)r * args.ld_out * EB) = val;
-                        }
-                    });
+            });
+            if constexpr (OUTK != 3) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t sb = stg_addr + kBufOff;
+                    tma_store_3d(&args.out_map[0], sb, fw, rbase + ps * SR, 0);
+                    if constexpr (OUTK == 0) tma_store_3d(&args.out_map[1], sb + KC * SR * 64, fw, rbase + ps * SR, 0);
+                    bulk_commit();
                 }
             }
-            __syncwarp();                                               // the buffer is free again
-#else
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_3d(&args.out_map[0], sb, fw, rbase + ps * SR, 0);
-                if constexpr (OUTK == 0) tma_store_3d(&args.out_map[1], sb + KC * SR * 64, fw, rbase + ps * SR, 0);
-                bulk_commit();
+        });
+        });
+        if constexpr (OUTK == 3) {
+            // ---- product rule of the blend (reference local_implicit_grid.py:57-61 + the jets), per feature ----
+            const uint32_t pa = row_addr + slot * kSlot + 160;
+            const float dx0 = __uint_as_float(lds_b32(pa + 48)), dx1 = __uint_as_float(lds_b32(pa + 52)),
+                        dx2 = __uint_as_float(lds_b32(pa + 56));
+            float bl[6];
+            bl[0] = acc[0];
+            bl[1] = fmaf(dx0, acc[4], acc[1]);
+            bl[2] = fmaf(dx1, acc[5], acc[2]);
+            bl[3] = fmaf(dx2, acc[6], acc[3]);
+            bl[4] = fmaf(2.f * dx1, acc[7], dx1 * dx1 * acc[9]);
+            bl[5] = fmaf(2.f * dx2, acc[8], dx2 * dx2 * acc[10]);
+            // ---- last linear layer: out[c][o] = sum_g W5[o][g] bl[c][g]: 24 values reduced over the 32 lanes so that
+            //      lane L ends with value L = c * 4 + o (multi-value butterfly: 31 shuffles) ----
+            float pv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pv[e] = e < 24 ? bl[e >> 2] * w5[e & 3] : 0.f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int e = 0; e < off; ++e) {
+                    const float send = up ? pv[e] : pv[e + off];
+                    const float keep = up ? pv[e + off] : pv[e];
+                    pv[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
             }
-#endif
-#endif
-        });
-        });
+            float total = pv[0];
+            // quarters (32-feature groups) that hold real features add up in a fixed order through smem
+            const int nq = min(4, (args.n_feat + 31) >> 5);
+            if (nq > 1) {
+                const uint32_t mine = row_addr + 768 + (n_items & 1) * 96;
+                if (lane < 24) sts_f32(mine + lane * 4, total);
+                named_bar_sync(1 + sub, 32 * nq);
+                if (quarter == 0 && lane < 24) {
+                    total = 0.f;
+                    // the warps of one `sub` sit at scratch indices 4 sub + ((quarter + 2) & 3); this is quarter 0 (index + 2)
+                    for (int qq = 0; qq < nq; ++qq)
+                        total += __uint_as_float(lds_b32(mine + (((qq + 2) & 3) - 2) * (int)kRowScratchFused + lane * 4));
+                }
+            }
+            const int ip = rbase >> 3;
+            const long long gp = args.p0 + ip;
+            const int c = lane >> 2, o = lane & 3;
+            if (quarter == 0 && lane < 24 && o < args.n_out && ip < args.pc && gp < args.total_pts) {
+                if (c < 4) total = fmaf(__ldg(args.b_last + o), sw[c], total);   // bias * sum of (d)weights
+                if (c == 0) args.y[gp * args.n_out + o] = total;
+                else args.jets[((long long)(c - 1) * args.total_pts + gp) * args.n_out + o] = total;
+            }
+        }
         }
         // rows of the item after next -> the slot `cur` just vacated (every lane has read its x values above)
         __syncwarp();
-        store_rows(slot, xv2, vv2);
+        store_rows(slot, xv2, vv2, pf2);
         __syncwarp();
         slot ^= 1;
+        ++n_items;
         cur = nxt;
-        nxt = nn;
+        if (cur.ok) nxt = next_item(cur);
     }
     if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
-#if !STPDE_EPI_DIRECT && !STPDE_EPI_DRAIN
     if (lane == 0) bulk_wait0();                                    // staging must stay valid until the last store has read it
-#endif
 }
 
-template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class TileFn, class HandBack>
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, bool CAN_FUSE, class TileFn, class HandBack>
 __device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
                                              int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
                                              uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
+    if constexpr (CAN_FUSE) {
+        if (args.last && args.fuse_final) {
+            fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 3>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+            return;
+        }
+    }
     if (args.last)
         fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 2>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
     else if (args.passes == 3)
@@ -867,13 +952,13 @@ __device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArg
 }
 
 // bytes of output staging a kernel mode needs (all 16 epilogue warps); the reverse modes still store directly
-template <int KC, int MODE>
+template <int KC, int MODE, bool SINGLE = false>
 __host__ __device__ constexpr uint32_t epi_staging_total() {
-    return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + kRowScratch) : 0u;
+    return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + (SINGLE ? kRowScratchFused : kRowScratch)) : 0u;
 }
 
 template <int KC, int SPEC = 0, int MODE = kModeFwd>
-__global__ void __maxnreg__(kMaxRegs)
+__global__ void __launch_bounds__(kThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
@@ -882,26 +967,29 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     constexpr int NRB = NR / 8;
     constexpr uint32_t kWBytes = kTileF * kBlockK * 2;        // one W plane tile
     constexpr uint32_t kABytes = N * kBlockK * 2;             // one activation plane tile
-    constexpr uint32_t kStageBytes = 2 * kWBytes + 2 * kABytes;
-    constexpr uint32_t kStaging = epi_staging_total<KC, MODE>();
+    constexpr uint32_t kRing = kStages * (2 * kWBytes + 2 * kABytes);   // operand ring: 2 stages of hi + lo planes ...
+    constexpr uint32_t kStaging = epi_staging_total<KC, MODE, true>();
     constexpr uint32_t kTmemCols = 512;
+    const bool three = args.passes == 3;
+    // ... or 4 stages when only the hi planes are loaded (single-pass mode): twice the bytes in flight per SM
+    const uint32_t stage_bytes = three ? 2 * kWBytes + 2 * kABytes : kWBytes + kABytes;
+    const int n_stages = min((int)(kRing / stage_bytes), kSingleMaxStages);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* staging = smem + kStages * kStageBytes;
+    uint8_t* staging = smem + kRing;
     uint64_t* bars = (uint64_t*)(staging + kStaging);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kStages;
-    uint64_t* tfull_bar = bars + 2 * kStages;
-    uint64_t* tempty_bar = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 4);
+    uint64_t* empty_bar = bars + kSingleMaxStages;
+    uint64_t* tfull_bar = bars + 2 * kSingleMaxStages;
+    uint64_t* tempty_bar = bars + 2 * kSingleMaxStages + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kSingleMaxStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_ftiles = (args.n_store + kTileF - 1) / kTileF;
     const int n_rtiles = (args.rows + NR - 1) / NR;
     const int n_tiles = n_ftiles * n_rtiles;
     const int kb_count = args.kp_in / kBlockK;
-    const bool three = args.passes == 3;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
@@ -910,7 +998,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int s = 0; s < kSingleMaxStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), kEpiWarps); }
             fence_barrier_init();
         }
@@ -930,21 +1018,21 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             for (int kb = 0; kb < kb_count; ++kb) {
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
                 const uint32_t fb = smem_u32(&full_bar[stage]);
-                const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                const uint32_t base = smem_u32(smem + stage * stage_bytes);
+                const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
                 if (elect_one()) {
-                    mbar_expect_tx(fb, three ? kStageBytes : (kWBytes + kABytes));
+                    mbar_expect_tx(fb, stage_bytes);
                     tma_load_2d(base, &map_w_hi, kb * kBlockK, f0, fb);
                     if (three) tma_load_2d(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
 #pragma unroll
                     for (int rb = 0; rb < NRB; ++rb) {
-                        tma_load_3d(base + 2 * kWBytes + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        tma_load_3d(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
                         if (three)
-                            tma_load_3d(base + 2 * kWBytes + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK,
-                                        r0 + rb * 8, 0, fb);
+                            tma_load_3d(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
                     }
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -960,9 +1048,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             for (int kb = 0; kb < kb_count; ++kb) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
                 tc_fence_after();
-                const uint32_t base = smem_u32(smem + stage * kStageBytes);
+                const uint32_t base = smem_u32(smem + stage * stage_bytes);
+                const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
                 const uint64_t w_hi = make_smem_desc(base), w_lo = make_smem_desc(base + kWBytes);
-                const uint64_t a_hi = make_smem_desc(base + 2 * kWBytes), a_lo = make_smem_desc(base + 2 * kWBytes + kABytes);
+                const uint64_t a_hi = make_smem_desc(a_base), a_lo = make_smem_desc(a_base + kABytes);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
@@ -977,7 +1066,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                     if (kb == kb_count - 1) umma_commit(smem_u32(&tfull_bar[buf]));
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -1011,8 +1100,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                 r0 = (t / n_ftiles) * NR;
                 return t < n_tiles;
             };
-            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
-                                                              smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
+            constexpr bool kCanFuse = MODE == kModeFwd && KC == 6 && SPEC == kSpecRb2;
+            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, kCanFuse>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+                                                              smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratchFused,
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         }
     }
@@ -1096,7 +1186,7 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
 }
 
 template <int KC, int MODE = kModeFwd, int SPEC = 0>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kMaxRegs)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ JetSpec spec, const __grid_constant__ LayerArgs args) {
@@ -1251,7 +1341,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
                 r0 = (t / n_ftiles) * NR;
                 return t < n_tiles;
             };
-            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
+            fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, false>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
                                                               smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         }

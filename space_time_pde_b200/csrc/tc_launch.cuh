@@ -43,7 +43,7 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     constexpr int NR = tc::rows_per_tile(KC);
     constexpr int N = KC * NR;
     const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) +
-                        tc::epi_staging_total<KC, tc::kModeFwd>() + 1024 + 256;
+                        tc::epi_staging_total<KC, tc::kModeFwd, true>() + 1024 + 256;
     static DeviceOnce configured;               // function attributes are per device
     if (configured.first_use()) {
         if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -103,7 +103,7 @@ static int launch_layer_mode(int num_sms, const CUtensorMap& w_hi, const CUtenso
     constexpr int NR = tc::rows_per_tile(KC);
     constexpr int N = KC * NR;
     const size_t smem = (size_t)tc::kStages * (2 * tc::kTileF * tc::kBlockK * 2 + 2 * N * tc::kBlockK * 2) +
-                        tc::epi_staging_total<KC, MODE>() + 1024 + 256;
+                        tc::epi_staging_total<KC, MODE, true>() + 1024 + 256;
     static DeviceOnce configured;
     if (configured.first_use()) {
         if (cudaFuncSetAttribute(tc::tc_layer_kernel<KC, SPEC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

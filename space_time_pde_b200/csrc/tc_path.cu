@@ -56,12 +56,15 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
 // One thread = 4 consecutive features of one row per iteration (8-byte stores, 256 B per warp and plane); the
 // per-feature constants live in registers, the next row's operands are prefetched while the current row is
-// evaluated (the kernel is latency-bound on the Vb gather otherwise).
-template <int KC>
+// evaluated.  The kernel is issue-bound (ncu r02: 87 % of the issue slots at 207 instructions per warp-row), so the
+// instruction count is what matters: THREE is a template parameter (the single-pass mode used to compute the lo plane
+// and throw it away), and the store addresses advance by pointer increments (one 64-bit add per plane and component)
+// instead of being rebuilt from (component, row) with 64-bit multiplies.
+template <int KC, bool THREE>
 __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
                                                                 int ld, const int* __restrict__ vtx,
                                                                 const float* __restrict__ xrel, const float* __restrict__ Wx,
-                                                                const float* __restrict__ Vb, int ncat, int three,
+                                                                const float* __restrict__ Vb, int ncat,
                                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                                 int* __restrict__ status) {
     constexpr int F = 4;
@@ -97,11 +100,12 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
     }
     const bool vec_ok = (n0 + F <= N) && (ncat % 4 == 0);
     const int n_first = spec.n_first;
+    const float* vb_col = Vb + n0;
     auto load_row = [&](int r, float* xr, float* vb) {
         const int rc = min(r, rows - 1);
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) xr[k] = __ldg(xrel + (int64_t)k * rows + rc);     // planes >= dim are zero
-        const float* vrow = Vb + (int64_t)__ldg(vtx + rc) * ncat + n0;
+        const float* vrow = vb_col + (int64_t)__ldg(vtx + rc) * ncat;
         if (vec_ok) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(vrow));
             vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w;
@@ -112,15 +116,20 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
     };
     float xr[kMaxDim], vb[F];
     const int rbase = blockIdx.y * 64 + rl;
-    if (rbase < rows) load_row(rbase, xr, vb);
+    if (rbase >= rows) return;
+    load_row(rbase, xr, vb);
+    // byte cursors of this thread's 4 features in component 0 of the current row; += 8 rows per iteration
+    const size_t plane_b = (size_t)rows * ld * sizeof(__half);
+    const size_t step_b = (size_t)8 * ld * sizeof(__half);
+    char* row_hi = reinterpret_cast<char*>(out_hi) + ((size_t)rbase * ld + n0) * sizeof(__half);
+    const ptrdiff_t lo_delta = THREE ? reinterpret_cast<char*>(out_lo) - reinterpret_cast<char*>(out_hi) : 0;
+    const int n_iter = min(8, (rows - rbase + 7) >> 3);
     dispatch_act(act, [&](auto act_c) {
     constexpr int kAct = decltype(act_c)::value;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const int r = rbase + 8 * j;
-        if (r >= rows) break;
+    for (int j = 0; j < n_iter; ++j) {
         float xr_n[kMaxDim], vb_n[F];
-        load_row(r + 8, xr_n, vb_n);                      // prefetch (clamped to a valid row)
+        load_row(rbase + 8 * j + 8, xr_n, vb_n);          // prefetch (clamped to a valid row)
         float s0[F], s1[F], s2[F];
 #pragma unroll
         for (int e = 0; e < F; ++e) {
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
             act_jet_fast(kAct, beta, z, s0[e], s1[e], s2[e]);
             smax = fmaxf(smax, fmaxf(fabsf(s0[e]), fmaxf(fabsf(s1[e]), fabsf(s2[e]))));
         }
+        char* p = row_hi;
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
             float x[F];
@@ -143,19 +153,19 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
 #pragma unroll
                 for (int e = 0; e < F; ++e) x[e] = s2[e] * coef[c][e];
             }
-            uint32_t ph[F / 2], pl[F / 2];
-#pragma unroll
-            for (int e = 0; e < F; e += 2) {
-                const __half2 h = __floats2half2_rn(x[e], x[e + 1]);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x[e] - hf.x, x[e + 1] - hf.y);
-                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+            *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
+                                                      *reinterpret_cast<const uint32_t*>(&h23));
+            if constexpr (THREE) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y);
+                const __half2 l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
+                *reinterpret_cast<uint2*>(p + lo_delta) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
+                                                                     *reinterpret_cast<const uint32_t*>(&l23));
             }
-            const int64_t off = ((int64_t)c * rows + r) * ld + n0;
-            *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(ph[0], ph[1]);
-            if (three) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pl[0], pl[1]);
+            p += plane_b;
         }
+        row_hi += step_b;
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) xr[k] = xr_n[k];
 #pragma unroll
@@ -243,6 +253,8 @@ const TcEnv& tc_env() {
         e.use_pair = p ? atoi(p) : 1;
         const char* w = getenv("STPDE_WAIT_NS");
         e.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u;
+        const char* f = getenv("STPDE_FUSE_FINAL");
+        e.fuse_final = f ? atoi(f) : 1;
         return e;
     }();
     return env;
@@ -357,22 +369,36 @@ template <int KC>
 static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                              int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
     dim3 grid((tc.ld0 + 127) / 128, (cb.rows + 63) / 64);
-    layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb, ncat,
-                                                    tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status);
+    if (tc.passes == 3)
+        layer0_jets_tc_kernel<KC, true><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb,
+                                                              ncat, tc.act[0][0], tc.act[0][1], tc.status);
+    else
+        layer0_jets_tc_kernel<KC, false><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb,
+                                                               ncat, tc.act[0][0], tc.act[0][1], tc.status);
 }
 
 void tc_launch_layer0_planes(int kc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
                              const float* Wx, const float* Vb, int ncat, int three, __half* out_hi, __half* out_lo,
                              int* status, cudaStream_t st) {
     dim3 grid((ld + 127) / 128, (cb.rows + 63) / 64);
-    STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
-                                                                              cb.xrel, Wx, Vb, ncat, three, out_hi, out_lo,
-                                                                              status)));
+    if (three) {
+        STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC, true><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
+                                                                                        cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)));
+    } else {
+        STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC, false><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
+                                                                                         cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)));
+    }
+}
+
+bool tc_can_fuse_final(const TcContext& tc, const JetSpec& spec, int dim, int n_out) {
+    const TcLayerPlan& L = tc.layer[tc.n_layers - 2];
+    const bool pair = tc.use_pair && L.n_feat >= 2 * tc::kTileF;
+    return tc_env().fuse_final && dim == 3 && spec_is_rb2(spec) && n_out <= 4 && !pair && L.n_feat <= tc::kTileF;
 }
 
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                  const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
-                 int np_last, cudaStream_t st) {
+                 int np_last, const TcFinal* fused_final, cudaStream_t st) {
     if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_prepare");
     {
         ProfScope ps(kSlotLayer0, st);
@@ -407,6 +433,21 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         int rc = STPDE_OK;
         ProfScope ps(kSlotGemm + l - 1, st);
         a.wait_ns = tc_env().wait_ns;
+        if (L.last && fused_final) {
+            a.fuse_final = 1;
+            a.n_out = fused_final->n_out;
+            a.ldw_last = fused_final->ldw;
+            a.w_last = fused_final->w_last;
+            a.b_last = fused_final->b_last;
+            a.pc = cb.pc;
+            a.p0 = fused_final->p0;
+            a.total_pts = fused_final->total_pts;
+            a.wfac = cb.wfac;
+            a.dfac = cb.dfac;
+            a.dxr = cb.dxr;
+            a.y = fused_final->y;
+            a.jets = fused_final->jets;
+        }
         rc = L.last ? tc_encode_out_maps(a, spec.kc, act_last, nullptr, true)
                     : tc_encode_out_maps(a, spec.kc, a.out_hi, tc.passes == 3 ? (void*)a.out_lo : nullptr, false);
         if (rc) return rc;

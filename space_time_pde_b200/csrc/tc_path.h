@@ -13,7 +13,20 @@ namespace stpde {
 struct TcEnv {
     int use_pair;
     uint32_t wait_ns;
+    int fuse_final;      // STPDE_FUSE_FINAL=0: keep the separate final_blend kernel
 };
+
+// Final linear layer + multilinear blend fused into the epilogue of the last hidden layer (inference, d = 3, the
+// Rayleigh-Benard jet set, <= 4 outputs, last hidden layer narrower than a CTA-pair tile): the launch writes y / jets.
+struct TcFinal {
+    const float* w_last;   // [O][ldw] padded last-layer weights
+    const float* b_last;   // [O]
+    int n_out, ldw;
+    float* y;
+    float* jets;
+    int64_t p0, total_pts;
+};
+bool tc_can_fuse_final(const struct TcContext& tc, const JetSpec& spec, int dim, int n_out);
 const TcEnv& tc_env();   // environment switches, read once per process
 
 struct TcLayerPlan {
@@ -45,7 +58,7 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
 // activations are written as fp32 [KC][rows][np_last] into act_last for final_blend.
 int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                  const float* Vb, int ncat, const int* cat_off, char* ws, const size_t* off_wx, float* act_last,
-                 int np_last, cudaStream_t st);
+                 int np_last, const TcFinal* fused_final, cudaStream_t st);
 
 const char* tc_last_error();
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out/s4
-export STPDE_LIB_PATH=$PWD/space_time_pde_b200/libstpde_tma1.so
+export STPDE_LIB_PATH=$PWD/space_time_pde_b200/libstpde_t.so
 timeout 300 python tools/quick_parity.py 2>&1 | tail -14 | tee gpurun_out/s4/parity.log
 for prec in fp16 fp16x3; do
   timeout 300 python tools/breakdown.py $prec 32 128 32 1000000 2>&1 | tail -1
