@@ -56,10 +56,9 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
 // layer 0 jets written as scaled fp16 hi/lo planes [KC][rows][ld] (pad columns n >= N are zero).
 // One thread = 4 consecutive features of one row per iteration (8-byte stores, 256 B per warp and plane); the
 // per-feature constants live in registers, the next row's operands are prefetched while the current row is
-// evaluated.  The kernel is issue-bound (ncu r02: 87 % of the issue slots at 207 instructions per warp-row), so the
-// instruction count is what matters: THREE is a template parameter (the single-pass mode used to compute the lo plane
-// and throw it away), and the store addresses advance by pointer increments (one 64-bit add per plane and component)
-// instead of being rebuilt from (component, row) with 64-bit multiplies.
+// evaluated (the kernel is latency-bound on the Vb gather otherwise).
+// THREE (lo plane written) is a template parameter: the single-pass mode used to compute the lo halves and drop them
+// (30 of its 207 instructions per warp-row; the kernel is issue-bound in that mode, ncu r02).
 template <int KC, bool THREE>
 __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
                                                                 int ld, const int* __restrict__ vtx,
@@ -100,12 +99,11 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
     }
     const bool vec_ok = (n0 + F <= N) && (ncat % 4 == 0);
     const int n_first = spec.n_first;
-    const float* vb_col = Vb + n0;
     auto load_row = [&](int r, float* xr, float* vb) {
         const int rc = min(r, rows - 1);
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) xr[k] = __ldg(xrel + (int64_t)k * rows + rc);     // planes >= dim are zero
-        const float* vrow = vb_col + (int64_t)__ldg(vtx + rc) * ncat;
+        const float* vrow = Vb + (int64_t)__ldg(vtx + rc) * ncat + n0;
         if (vec_ok) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(vrow));
             vb[0] = a.x; vb[1] = a.y; vb[2] = a.z; vb[3] = a.w;
@@ -116,20 +114,15 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
     };
     float xr[kMaxDim], vb[F];
     const int rbase = blockIdx.y * 64 + rl;
-    if (rbase >= rows) return;
-    load_row(rbase, xr, vb);
-    // byte cursors of this thread's 4 features in component 0 of the current row; += 8 rows per iteration
-    const size_t plane_b = (size_t)rows * ld * sizeof(__half);
-    const size_t step_b = (size_t)8 * ld * sizeof(__half);
-    char* row_hi = reinterpret_cast<char*>(out_hi) + ((size_t)rbase * ld + n0) * sizeof(__half);
-    const ptrdiff_t lo_delta = THREE ? reinterpret_cast<char*>(out_lo) - reinterpret_cast<char*>(out_hi) : 0;
-    const int n_iter = min(8, (rows - rbase + 7) >> 3);
+    if (rbase < rows) load_row(rbase, xr, vb);
     dispatch_act(act, [&](auto act_c) {
     constexpr int kAct = decltype(act_c)::value;
 #pragma unroll 1
-    for (int j = 0; j < n_iter; ++j) {
+    for (int j = 0; j < 8; ++j) {
+        const int r = rbase + 8 * j;
+        if (r >= rows) break;
         float xr_n[kMaxDim], vb_n[F];
-        load_row(rbase + 8 * j + 8, xr_n, vb_n);          // prefetch (clamped to a valid row)
+        load_row(r + 8, xr_n, vb_n);                      // prefetch (clamped to a valid row)
         float s0[F], s1[F], s2[F];
 #pragma unroll
         for (int e = 0; e < F; ++e) {
@@ -139,7 +132,6 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
             act_jet_fast(kAct, beta, z, s0[e], s1[e], s2[e]);
             smax = fmaxf(smax, fmaxf(fabsf(s0[e]), fmaxf(fabsf(s1[e]), fabsf(s2[e]))));
         }
-        char* p = row_hi;
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
             float x[F];
@@ -153,19 +145,21 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
 #pragma unroll
                 for (int e = 0; e < F; ++e) x[e] = s2[e] * coef[c][e];
             }
-            const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
-            *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01),
-                                                      *reinterpret_cast<const uint32_t*>(&h23));
-            if constexpr (THREE) {
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y);
-                const __half2 l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
-                *reinterpret_cast<uint2*>(p + lo_delta) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
-                                                                     *reinterpret_cast<const uint32_t*>(&l23));
+            uint32_t ph[F / 2], pl[F / 2];
+#pragma unroll
+            for (int e = 0; e < F; e += 2) {
+                const __half2 h = __floats2half2_rn(x[e], x[e + 1]);
+                ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                if constexpr (THREE) {
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(x[e] - hf.x, x[e + 1] - hf.y);
+                    pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+                }
             }
-            p += plane_b;
+            const int64_t off = ((int64_t)c * rows + r) * ld + n0;
+            *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(ph[0], ph[1]);
+            if constexpr (THREE) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pl[0], pl[1]);
         }
-        row_hi += step_b;
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) xr[k] = xr_n[k];
 #pragma unroll

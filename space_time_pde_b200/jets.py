@@ -350,15 +350,17 @@ class FusedJetQuery(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, grid, q, lo, hi, act, act_param_t, spec, precision, n_layers, *params):
-        ctx.ddp = None
-        if isinstance(n_layers, tuple):          # (n_layers, DistributedDataParallel wrapper of the decoder)
-            n_layers, ctx.ddp = n_layers
+        ctx.ddp, ctx.train = None, True
+        if isinstance(n_layers, tuple):          # (n_layers, DistributedDataParallel wrapper | None, caller's grad mode)
+            n_layers, ctx.ddp, ctx.train = n_layers
         Ws, bs = params[:n_layers], params[n_layers:]
         beta = float(act_param_t.detach()) if act_param_t is not None else 1.0
         needs = ctx.needs_input_grad
         stash_out = None
-        if (needs[0] or any(needs[9:])) and fused_backward_supported(q, spec, n_layers, needs[1],
-                                                                    act_param_t is not None and needs[5]):
+        # (needs_input_grad is True for parameters even under torch.no_grad(): the grad mode of the CALLER decides
+        #  whether this is a training forward - inference of a small batch must not pay for keeping the planes)
+        if ctx.train and (needs[0] or any(needs[9:])) and fused_backward_supported(q, spec, n_layers, needs[1],
+                                                                                  act_param_t is not None and needs[5]):
             stash_out = []            # training forward: keep the operand planes for the backward when they fit
         y, jets = raw_forward(grid, q, lo, hi, Ws, bs, act, beta, spec, precision, stash_out=stash_out)
         ctx.stash_token = stash_out[0] if stash_out else 0
@@ -449,6 +451,6 @@ def fused_query(grid: torch.Tensor, q: torch.Tensor, xmin, xmax, layers, act: st
     lo, hi = bounds_tensors(xmin, xmax, q.shape[-1], q.device)
     Ws = [l.weight for l in layers]
     bs = [l.bias for l in layers]
-    nl = len(layers) if ddp is None else (len(layers), ddp)
+    nl = (len(layers), ddp, torch.is_grad_enabled())
     y, jets = FusedJetQuery.apply(grid, q, lo, hi, act, act_param, spec, precision, nl, *Ws, *bs)
     return y, (jets if spec.n_jet else None)
