@@ -112,7 +112,12 @@ typedef struct stpde_desc {
     int32_t precision;
     float xmin[STPDE_MAX_DIM];          /* float32 bounds exactly as the reference forms them */
     float xmax[STPDE_MAX_DIM];
-    int32_t reserved[8];                /* [0]: backward only, extra headroom bits of the adjoint scale (0 = default) */
+    int32_t reserved[8];                /* [0]: backward only, extra headroom bits of the adjoint scale (0 = default)
+                                         * [1]: stpde_jet_forward only, 1 = the call-invariant part of the workspace (packed /
+                                         *      split weights, per-vertex latent + bias table) is still valid from the
+                                         *      previous call on the SAME workspace with the same decoder weights, latent
+                                         *      grid, shapes and precision: the per-call setup kernels are skipped (the
+                                         *      caller guarantees it; evaluation loops over pseudo-batches) */
 } stpde_desc_t;
 
 int stpde_version(void);

@@ -17,8 +17,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("STPDE_LIB_PATH") or os.path.join(HERE, "libstpde.so")   # (override: kernel experiments)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "simt_kernels.cu", "bwd_kernels.cu", "tc_path.cu", "tc_bwd.cu", "tc_layers_a.cu", "tc_layers_b.cu",
-           "tc_bwd_a.cu", "tc_bwd_b.cu", "tc_bwd_c.cu", "profile.cu"]
+# the tensor-core kernel families are instantiated for K = 1..10 jet components: one translation unit per family and
+# half of the K range (heaviest first, so that the parallel build ends together)
+SOURCES = [f"{fam}_{half}.cu" for fam in ("tc_bwd_a_pair", "tc_bwd_a_single", "tc_layers_a", "tc_layers_b", "tc_bwd_b_pair",
+                                           "tc_bwd_b_single", "tc_bwd_c_pair", "tc_bwd_c_single") for half in ("hi", "lo")] + \
+          ["api.cu", "simt_kernels.cu", "bwd_kernels.cu", "tc_path.cu", "tc_bwd.cu", "profile.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -87,7 +90,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.run(cmd, check=True, cwd=CSRC)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), (os.cpu_count() or 8) + 2)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     link = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcuda"]
     if verbose:

@@ -242,21 +242,25 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
         net.B[l] = B[l];
     }
     float* Vb = (float*)(ws + P.off_vb);
-    prof_begin(kSlotSetup, st);
-    for (int l = 0; l < P.n_layers; ++l) {
-        float* wh = l >= 1 ? (float*)(ws + P.off_wh[l]) : nullptr;
-        float* wx = l < P.n_layers - 1 ? (float*)(ws + P.off_wx[l]) : nullptr;
-        int rows_w = (l == P.n_layers - 1) ? P.widths[l] : P.np64[l];
-        if (l >= 1) launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, rows_w, P.kp[l], wh, wx, st);
-        else launch_pack_weights(W[l], P.widths[l], P.in_features[l], 0, dim, 0, 1, nullptr, wx, st);
+    // reserved[1] = 1: the caller vouches that the call-invariant region (packed / split weights, Vb) is still valid
+    const bool reuse_setup = d->reserved[1] == 1;
+    if (!reuse_setup) {
+        prof_begin(kSlotSetup, st);
+        for (int l = 0; l < P.n_layers; ++l) {
+            float* wh = l >= 1 ? (float*)(ws + P.off_wh[l]) : nullptr;
+            float* wx = l < P.n_layers - 1 ? (float*)(ws + P.off_wx[l]) : nullptr;
+            int rows_w = (l == P.n_layers - 1) ? P.widths[l] : P.np64[l];
+            if (l >= 1) launch_pack_weights(W[l], P.widths[l], P.in_features[l], P.kh[l], dim, rows_w, P.kp[l], wh, wx, st);
+            else launch_pack_weights(W[l], P.widths[l], P.in_features[l], 0, dim, 0, 1, nullptr, wx, st);
+        }
+        launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
+        prof_end(kSlotSetup, st, P.n_layers + 1);
     }
-    launch_vertex_bias(P.geom, P.nvert_total, net, grid, Vb, st);
-    prof_end(kSlotSetup, st, P.n_layers + 1);
 
     TcContext tc;
     if (use_tc) {
         int rc = tc_prepare(tc, d->precision, P.n_layers, P.widths, P.in_features, W, ws + P.off_tc, tc_chunk,
-                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, st);
+                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, !reuse_setup, st);
         if (rc) return fail(rc, "%s", tc_last_error());
     }
 

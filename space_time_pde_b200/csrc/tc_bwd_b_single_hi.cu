@@ -1,0 +1,3 @@
+// tc_bwd_b_single: K = 6..10, Rayleigh-Benard specialisation, dispatcher (see tc_bwd_b_single.inc)
+#define STPDE_KC_HALF 1
+#include "tc_bwd_b_single.inc"

@@ -10,6 +10,28 @@ int tc_fail(int code, const char* msg);
 int tc_launch_layer(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 int tc_launch_layer_pair(int kc, const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a, cudaStream_t st);
 
+// The K = 1..10 instantiations of every kernel family are split over two translation units (K <= 5 / K >= 6) so that
+// the build parallelises: *_lo.cu / *_hi.cu include the family's .inc with STPDE_KC_HALF 0 / 1.
+#define STPDE_TC_DISPATCH_KC_LO(kc, CALL)              \
+    switch (kc) {                                      \
+        case 1: { constexpr int KC = 1; CALL; } break; \
+        case 2: { constexpr int KC = 2; CALL; } break; \
+        case 3: { constexpr int KC = 3; CALL; } break; \
+        case 4: { constexpr int KC = 4; CALL; } break; \
+        default: { constexpr int KC = 5; CALL; } break; \
+    }
+#ifdef STPDE_ONLY_RB2
+#define STPDE_TC_DISPATCH_KC_HI(kc, CALL) { constexpr int KC = 6; CALL; }
+#else
+#define STPDE_TC_DISPATCH_KC_HI(kc, CALL)              \
+    switch (kc) {                                      \
+        case 6: { constexpr int KC = 6; CALL; } break; \
+        case 7: { constexpr int KC = 7; CALL; } break; \
+        case 8: { constexpr int KC = 8; CALL; } break; \
+        case 9: { constexpr int KC = 9; CALL; } break; \
+        default: { constexpr int KC = 10; CALL; } break; \
+    }
+#endif
 #ifdef STPDE_ONLY_RB2   // kernel experiments (tools/build_variant.sh): instantiate K = 6 only, builds in a fraction of the time
 #define STPDE_TC_DISPATCH_KC(kc, CALL) { constexpr int KC = 6; CALL; }
 #else

@@ -293,7 +293,7 @@ void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int
 
 int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-               int* status, cudaStream_t st) {
+               int* status, bool split_weights, cudaStream_t st) {
     if (!encode_fn()) return tc_fail(STPDE_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
     if (n_layers < 3) return tc_fail(STPDE_EUNSUPPORTED, "the tensor-core path needs at least one hidden contraction");
     memset(&tc, 0, sizeof(tc));
@@ -314,7 +314,7 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
 
     tc.wscale = (float*)fixed_ws;
     tc.absmax = (unsigned*)(fixed_ws + 512);
-    cudaMemsetAsync(tc.absmax, 0, 256, st);
+    if (split_weights) cudaMemsetAsync(tc.absmax, 0, 256, st);
     size_t off = 1024;
     int me, mo;
     plane_lds(n_layers, widths, me, mo);
@@ -329,9 +329,7 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     tc.ld0 = round_up(widths[0], 64);
     tc.n0 = widths[0];
 
-    prof_begin(kSlotSetup, st);
-    const int NR = tc::rows_per_tile(kc);
-    (void)NR;
+    if (split_weights) prof_begin(kSlotSetup, st);
     for (int l = 1; l <= n_layers - 2; ++l) {
         TcLayerPlan& L = tc.layer[l];
         L.n_feat = widths[l];
@@ -344,18 +342,20 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
         L.w_hi_ptr = (__half*)(fixed_ws + off); off += plane;
         L.w_lo_ptr = (__half*)(fixed_ws + off); off += plane;
         const int kh = widths[l - 1];
-        absmax_kernel<<<148, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, tc.absmax + l);
-        split_weights_kernel<<<148 * 4, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, L.np128, L.kp_in,
-                                                      tc.absmax + l, tc.wscale + l, L.w_hi_ptr, L.w_lo_ptr);
+        if (split_weights) {     // (a call that reuses the previous call's setup finds the planes and scales in place)
+            absmax_kernel<<<148, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, tc.absmax + l);
+            split_weights_kernel<<<148 * 4, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, L.np128, L.kp_in,
+                                                          tc.absmax + l, tc.wscale + l, L.w_hi_ptr, L.w_lo_ptr);
+        }
         int rc = make_map_2d(&L.w_hi, L.w_hi_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
         rc |= make_map_2d(&L.w_lo, L.w_lo_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
         __half* in_hi = tc.act[(l - 1) & 1][0];
         __half* in_lo = tc.act[(l - 1) & 1][1];
         rc |= make_map_3d(&L.a_hi, in_hi, L.kp_in, rows, kc, tc::kBlockK, 8, kc);
         rc |= make_map_3d(&L.a_lo, in_lo, L.kp_in, rows, kc, tc::kBlockK, 8, kc);
-        if (rc) { prof_end(kSlotSetup, st, 0); return tc_fail(STPDE_ECUDA, "cuTensorMapEncodeTiled failed"); }
+        if (rc) { if (split_weights) prof_end(kSlotSetup, st, 0); return tc_fail(STPDE_ECUDA, "cuTensorMapEncodeTiled failed"); }
     }
-    prof_end(kSlotSetup, st, 2 * (n_layers - 2));
+    if (split_weights) prof_end(kSlotSetup, st, 2 * (n_layers - 2));
     return STPDE_OK;
 }
 

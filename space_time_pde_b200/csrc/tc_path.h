@@ -52,7 +52,7 @@ size_t tc_per_point_bytes(int n_layers, const int* widths, int kc, int ncorner);
 // Once per call: split the hidden-layer weights into scaled fp16 hi/lo planes, build the TMA maps.
 int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-               int* status, cudaStream_t st);
+               int* status, bool split_weights, cudaStream_t st);
 
 // Per chunk: layer 0 (closed form) -> hidden layers on the tensor cores; the last hidden layer's
 // activations are written as fp32 [KC][rows][np_last] into act_last for final_blend.

@@ -134,3 +134,39 @@ def test_config5_sweep_shape_forward_and_backward(dev):
         errs[f"b{l}"] = rel_linf(gB[l].cpu().numpy(), rB[l].cpu().numpy())
     print({k: f"{v:.1e}" for k, v in errs.items()})
     assert max(errs.values()) < 5e-5, errs
+
+
+def test_setup_cache_for_inference_loops(dev):
+    """Consecutive no-grad calls against the same latent grid and decoder skip the per-call setup kernels
+    (evaluation.py's pseudo-batch loop); an in-place weight update (optimizer style) or a new grid invalidates the cache."""
+    from space_time_pde_b200 import _lib
+    torch.manual_seed(11)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=16, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 4, 6, 5, 16, device=dev) * 0.5
+    q = torch.rand(1, 2000, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    lib = _lib.load()
+    jets.release_workspaces()
+
+    def run(points):
+        lib.stpde_profile_enable(1)
+        _lib.profile_read()
+        with torch.no_grad():
+            y, res = layer(points)
+        prof = _lib.profile_read()
+        lib.stpde_profile_enable(0)
+        return y, res, prof.get("setup", (0.0, 0))[1]
+
+    y1, r1, n1 = run(q)
+    y2, r2, n2 = run(q)
+    y3, _, n3 = run(q[:, :700])                                  # another pseudo-batch, same grid and weights
+    assert n1 > 0 and n2 == 0 and n3 == 0
+    assert torch.equal(y1, y2) and all(torch.equal(r1[k], r2[k]) for k in r1) and torch.equal(y3, y1[:, :700])
+    with torch.no_grad():
+        model.fc[5].bias.add_(1.0)                               # in-place update bumps the version: setup runs again
+    y4, _, n4 = run(q)
+    assert n4 > 0 and float((y4 - y1 - 1.0).abs().max()) < 1e-5
+    grid = grid * 1.0                                            # a new tensor (new storage): setup runs again
+    _, _, n5 = run(q)
+    assert n5 > 0
