@@ -268,12 +268,14 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         a.g_wx_ld = in_features[l - 1];
         ProfScope ps(kSlotDgrad + l - 1, st);
         const bool wide = L.kh >= 2 * tc::kTileF && tc.use_pair_wide;   // M extent of the dgrad = features of layer l-1
-        int rc;
+        int rc = STPDE_OK;
         if (l >= 2) {
             a.z_in = tc.layer[l - 1].z;
             a.ldz = tc.layer[l - 1].ldz;
             a.out_hi = tc.layer[l - 1].zb[0];
             a.out_lo = tc.layer[l - 1].zb[1];
+            rc = tc_encode_out_maps(a, spec.kc, a.out_hi, tc.passes == 3 ? (void*)a.out_lo : nullptr, false, true);
+            if (rc) return rc;
             rc = wide ? tc_launch_pair_bwd(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st)
                       : tc_launch_single_bwd(spec.kc, tc.num_sms, L.wt_hi, L.wt_lo, L.zb_hi, L.zb_lo, spec, a, st);
         } else {

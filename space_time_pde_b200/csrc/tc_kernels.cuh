@@ -56,6 +56,9 @@ __host__ __device__ constexpr int stage_rows_base(int kc) {
 __host__ __device__ constexpr int stage_rows(int kc) {
     return stage_rows_base(kc) / STPDE_EPI_SR_DIV > 0 ? stage_rows_base(kc) / STPDE_EPI_SR_DIV : 1;
 }
+// reverse mode: the rows of a staging pass must cover one TMEM chunk (2 rows for K > 3)
+__host__ __device__ constexpr int stage_rows_bwd(int kc) { return stage_rows(kc) < 2 && kc > 3 ? 2 : stage_rows(kc); }
+__host__ __device__ constexpr uint32_t epi_stage_bytes_bwd(int kc) { return (uint32_t)kc * stage_rows_bwd(kc) * 128u; }
 __host__ __device__ constexpr uint32_t epi_stage_bytes(int kc) {
     return (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;
 }
@@ -314,255 +317,6 @@ constexpr int kModeFwd = 0;       // forward layer (inference)
 constexpr int kModeFwdSave = 1;   // forward layer that also stores its pre-activations (recompute pass of the backward)
 constexpr int kModeBwd = 2;       // dgrad of layer l (W_l^T . zbar_l) + reverse jet activation of layer l-1 >= 1
 constexpr int kModeBwd0 = 3;      // dgrad of layer 1 + reverse of the closed-form layer 0
-
-// One tile of the reverse-mode epilogue (shared by the CTA-pair and the single-CTA kernel).
-// The accumulator holds S * 2^sw * abar[c][r][g]: the adjoint of the activations of the layer BELOW the contraction
-// (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with the saved z planes
-// and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the closed-form layer 0 (nothing below it:
-// only the parameter adjoints are accumulated).  Rows are processed in steps of H (4 or 2).
-//   f0        first feature of this CTA's 128-feature slice of the tile, r0 first row of the tile
-//   taddr     TMEM address of the accumulator (lane quarter and buffer already applied)
-//   next_f0   first of this WARP's 32 features in its next tile (or -1), next_r0 that tile's first row (L2 prefetch)
-template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ>
-__device__ __forceinline__ void bwd_epilogue_tile(const JetSpec& spec, const LayerArgs& args, int f0, int r0, int quarter,
-                                                  int sub, int lane, uint32_t taddr, uint32_t tfull_addr,
-                                                  uint32_t tfull_parity, int next_f0, int next_r0) {
-    constexpr int H = (MODE == kModeBwd0 || KC <= 3) ? 4 : 2;  // rows per step (register budget: 96 per thread)
-    constexpr int PC = (MODE == kModeBwd) ? KC : 1;            // prefetched values per row
-    // MODE 3 prefetches the next step's z0 into registers (dependent vertex gather); MODE 2 relies on the L2
-    // prefetch of the next tile - a register double buffer of K values per row spills inside the hot loop and the
-    // spill store then waits for the load it was meant to hide.
-    constexpr bool kPrefetch = (MODE == kModeBwd0);
-    const bool three = args.passes == 3;
-    const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
-    const int64_t plane = (int64_t)args.rows * args.ld_out;
-    const int64_t zplane = (int64_t)args.rows * args.ldz;
-    const int n_first = spec.n_first;
-    const bool swish_beta_rt = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
-    const int g = f0 + quarter * 32 + lane;
-    const bool g_store = g < args.n_store;
-    const bool g_ok = g < args.n_feat;
-    float bsum = 0.f;                                       // Swish only: d loss / d beta of this thread's elements
-    float G[kMaxDim], A[KC];                                // per-tile partial sums of the coordinate-column adjoint
-#pragma unroll
-    for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
-#pragma unroll
-    for (int c = 0; c < KC; ++c) A[c] = 0.f;
-    float wx[kMaxDim], cf[KC];                              // MODE 3: layer-0 coordinate columns / jet coefficients
-#pragma unroll
-    for (int k = 0; k < kMaxDim; ++k)
-        wx[k] = (MODE == kModeBwd0 && k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
-#pragma unroll
-    for (int c = 0; c < KC; ++c) {
-        float wa = 1.f, wb = 1.f;
-        if constexpr (MODE == kModeBwd0) {
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) {
-                if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
-                if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
-                if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
-            }
-        }
-        cf[c] = wa * wb;
-    }
-    // operands of one half block: MODE 2 the saved pre-activations, MODE 3 the recomputed z0 of layer 0
-    auto fetch = [&](int row0, float (&pz)[PC][H]) {
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-            const int rc = min(row0 + j, args.rows - 1);
-            if constexpr (MODE == kModeBwd) {
-#pragma unroll
-                for (int c = 0; c < KC; ++c)
-                    pz[c][j] = g_ok ? __ldg(args.z_in + (int64_t)c * zplane + (int64_t)rc * args.ldz + g) : 0.f;
-            } else {
-                float z0 = g_ok ? __ldg(args.Vb + (int64_t)__ldg(args.vtx + rc) * args.ncat + args.cat_off + g) : 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k)
-                    if (k < args.dim) z0 = fmaf(wx[k], __ldg(args.xrel + (int64_t)k * args.rows + rc), z0);
-                pz[0][j] = z0;
-            }
-        }
-    };
-    float zc[PC][H], zn[PC][H];
-    if (kPrefetch && sub < NRB) fetch(r0 + sub * 8, zc);
-    if constexpr (MODE == kModeBwd) {
-        // The z planes stream from HBM (no reuse): pull the lines of this warp's NEXT tile into L2 now, one
-        // 128-byte line (32 features of one row and component) per lane.
-        if (next_f0 >= 0 && next_f0 < args.n_feat) {
-            for (int rb = sub; rb < NRB; rb += EPI_PQ) {
-                const int r0n = next_r0 + rb * 8;
-                for (int idx = lane; idx < KC * 8; idx += 32) {
-                    const int rn = min(r0n + (idx & 7), args.rows - 1);
-                    prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + next_f0);
-                }
-            }
-        }
-    }
-    mbar_wait(tfull_addr, tfull_parity, args.status, args.wait_ns);
-    tc_fence_after();
-    float amax = 0.f;
-#pragma unroll 1
-    for (int rb = sub; rb < NRB; rb += EPI_PQ) {
-#pragma unroll 1
-        for (int h = 0; h < 8 / H; ++h) {                  // rolled: the unrolled epilogue overflowed the i-cache
-            const int rbase = r0 + rb * 8 + h * H;
-            uint32_t v[KC][H];
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                if constexpr (H == 4) tmem_ld_x4(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
-                else tmem_ld_x2(taddr + rb * (8 * KC) + c * 8 + h * H, v[c]);
-            }
-            if constexpr (kPrefetch) {
-                if (h + 1 < 8 / H) fetch(rbase + H, zn);
-                else if (rb + EPI_PQ < NRB) fetch(r0 + (rb + EPI_PQ) * 8, zn);
-            } else {
-                fetch(rbase, zc);
-            }
-            tmem_wait_ld();
-            dispatch_act(args.act, [&](auto act_c) {
-            constexpr int kAct = decltype(act_c)::value;
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                const int r = rbase + j;
-                const bool r_ok = r < args.rows;
-                const int rc = min(r, args.rows - 1);
-                const int vrow = __ldg(args.vtx + rc);        // L1-resident: shared by every feature of the tile
-                float xr[kMaxDim];
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k) xr[k] = k < args.dim ? __ldg(args.xrel + (int64_t)k * args.rows + rc) : 0.f;
-                float ab[KC];
-#pragma unroll
-                for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
-                float s1, s2, s3, z0b;
-                act_d123_fast(kAct, args.beta, zc[0][j], s1, s2, s3);
-                if constexpr (MODE == kModeBwd) {
-                    float zb[KC];
-                    float u = 0.f, w3 = 0.f;
-                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) { u = fmaf(ab[c], zc[c][j], u); zb[c] = s1 * ab[c]; }
-                        const float p4 = ab[4] * zc[2][j], p5 = ab[5] * zc[3][j];
-                        w3 = fmaf(p4, zc[2][j], p5 * zc[3][j]);
-                        zb[2] = fmaf(2.f * s2, p4, zb[2]);
-                        zb[3] = fmaf(2.f * s2, p5, zb[3]);
-                    } else {
-                        float cross[STPDE_MAX_FIRST];
-#pragma unroll
-                        for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) {
-                            u = fmaf(ab[c], zc[c][j], u);
-                            zb[c] = s1 * ab[c];
-                            if (c > n_first) {                 // second order (warp-uniform): parents za, zp
-                                float za = 0.f, zp = 0.f;
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
-                                    if (1 + k < KC) {
-                                        za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
-                                        zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
-                                    }
-                                }
-                                w3 = fmaf(ab[c] * za, zp, w3);
-#pragma unroll
-                                for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                                    if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < STPDE_MAX_FIRST; ++k)
-                            if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
-                    }
-                    z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
-                    zb[0] = z0b;
-                    if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
-                        float sb0, sb1, sb2;
-                        swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
-                        bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
-                    }
-#pragma unroll
-                    for (int c = 1; c < KC; ++c) A[c] += zb[c];
-                    if (g_store && r_ok) {
-                        const int64_t off = (int64_t)r * args.ld_out + g;
-                        __half* ph = args.out_hi + off;
-                        __half* pl = args.out_lo + off;
-#pragma unroll
-                        for (int c = 0; c < KC; ++c) {
-                            const float xs = zb[c];
-                            amax = fmaxf(amax, fabsf(xs));
-                            const __half hi = __float2half_rn(xs);
-                            *ph = hi;
-                            if (three) *pl = __float2half_rn(xs - __half2float(hi));
-                            ph += plane; pl += plane;
-                        }
-                    }
-                } else {
-                    // layer 0: a_c = sigma^(order_c)(z0) * cf_c
-                    float t1 = 0.f, t2 = 0.f;
-                    if constexpr (SPEC == kSpecRb2 && KC == 6) {
-                        t1 = fmaf(ab[1], cf[1], fmaf(ab[2], cf[2], ab[3] * cf[3]));
-                        t2 = fmaf(ab[4], cf[4], ab[5] * cf[5]);
-#pragma unroll
-                        for (int c = 1; c < 4; ++c) A[c] = fmaf(ab[c], s1, A[c]);
-                        A[4] = fmaf(ab[4], s2, A[4]);
-                        A[5] = fmaf(ab[5], s2, A[5]);
-                    } else {
-#pragma unroll
-                        for (int c = 1; c < KC; ++c) {
-                            const float pc = ab[c] * cf[c];
-                            if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
-                            else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
-                        }
-                    }
-                    z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
-                    if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
-                        float sb0, sb1, sb2;
-                        swish_dbeta(args.beta, zc[0][j], sb0, sb1, sb2);
-                        bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
-                if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
-            }
-            });
-            if constexpr (kPrefetch) {
-#pragma unroll
-                for (int c = 0; c < PC; ++c)
-#pragma unroll
-                    for (int j = 0; j < H; ++j) zc[c][j] = zn[c][j];
-            }
-        }
-    }
-    if (g_ok) {
-        // fold the per-component sums into the coordinate columns (once per tile)
-#pragma unroll
-        for (int c = 1; c < KC; ++c) {
-#pragma unroll
-            for (int k = 0; k < kMaxDim; ++k) {
-                if (spec.kind[c] == 1 && k == spec.dir[c]) G[k] += A[c];
-                if constexpr (MODE == kModeBwd0) {
-                    if (spec.kind[c] == 2) {
-                        const int da = spec.dir[spec.pa[c]], db = spec.dir[spec.pb[c]];
-                        float wda = 0.f, wdb = 0.f;
-#pragma unroll
-                        for (int kk = 0; kk < kMaxDim; ++kk) { if (kk == da) wda = wx[kk]; if (kk == db) wdb = wx[kk]; }
-                        if (k == da) G[k] = fmaf(A[c], wdb, G[k]);
-                        if (k == db) G[k] = fmaf(A[c], wda, G[k]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kMaxDim; ++k)
-            if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
-    }
-    if (swish_beta_rt) {
-        for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
-        if (lane == 0) atomicAdd(args.g_beta, bsum);
-    }
-    if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
-}
-
 
 // Forward epilogue of one epilogue warp over ALL its tiles (shared by the CTA-pair and the single-CTA kernel):
 // TMEM -> skip term + jet activation -> next layer's operand planes.
@@ -951,10 +705,372 @@ __device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArg
         fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
 }
 
+// Reverse-mode epilogue of one epilogue warp over ALL its tiles (MODE 2 / 3), same structure as fwd_epilogue_loop:
+// software-pipelined row operands through a 2-slot smem scratch, the Vb gather of the NEXT item in flight (MODE 3
+// recomputes z_0 of layer 0 from it), accumulator hand-back right after the last tcgen05.wait::ld, and - MODE 2 - the
+// zbar planes staged in shared memory with immediate-offset stores and written by TMA.
+// The accumulator holds S * 2^sw * abar[c][r][g]: the adjoint of the activations of the layer BELOW the contraction
+// (feature g = TMEM lane).  MODE 2 turns it into the adjoint of that layer's pre-activations with the saved z planes
+// and writes the next dgrad / wgrad operand planes; MODE 3 does the same for the closed-form layer 0 (nothing below it:
+// only the parameter adjoints are accumulated).  The per-thread partial sums of the coordinate-column adjoint (G, A)
+// and of the Swish beta adjoint live in registers across ALL tiles of a feature tile and are flushed with atomics once.
+// OUTK: 0 = zbar hi + lo planes, 1 = hi plane only (single-pass reverse sweep), ignored in MODE 3.
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class TileFn, class HandBack>
+__device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
+                                                  uint32_t row_addr, int quarter, int sub, int lane, uint32_t tmem_q,
+                                                  int n_cols, uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
+    constexpr bool kBwd0 = MODE == kModeBwd0;
+    constexpr uint32_t kSlot = 192;
+    constexpr int SRB = stage_rows_bwd(KC);
+    constexpr int SR = (OUTK == 1 && SRB < 8) ? 2 * SRB : SRB;      // rows per staging pass (MODE 2)
+    constexpr int HMAX = (kBwd0 || KC <= 3) ? 4 : 2;               // rows per TMEM chunk (register budget)
+    constexpr int TL = kBwd0 ? HMAX : (SR < HMAX ? SR : HMAX);
+    constexpr int NPASS = kBwd0 ? 1 : 8 / SR;
+    constexpr int CHUNKS = kBwd0 ? 8 / TL : SR / TL;               // chunks per pass
+    const bool has_blocks = sub < NRB;
+    const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
+    const int64_t zplane = (int64_t)args.rows * args.ldz;
+    const int n_first = spec.n_first;
+    const bool swish_beta_rt = args.act == STPDE_ACT_SWISH && args.g_beta != nullptr;
+
+    // ---- per-feature state ----
+    int cur_f0 = -1, g = 0;
+    bool g_ok = false, live = false;
+    float wx[kMaxDim], cf[KC];                              // MODE 3: layer-0 coordinate columns / jet coefficients
+    float G[kMaxDim], A[KC], bsum = 0.f;                    // partial sums of the coordinate-column / beta adjoints
+#pragma unroll
+    for (int k = 0; k < kMaxDim; ++k) { G[k] = 0.f; wx[k] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { A[c] = 0.f; cf[c] = 1.f; }
+    auto flush_sums = [&]() {
+        if (cur_f0 >= 0 && g_ok) {
+#pragma unroll
+            for (int c = 1; c < KC; ++c) {
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k) {
+                    if (spec.kind[c] == 1 && k == spec.dir[c]) G[k] += A[c];
+                    if constexpr (kBwd0) {
+                        if (spec.kind[c] == 2) {
+                            const int da = spec.dir[spec.pa[c]], db = spec.dir[spec.pb[c]];
+                            float wda = 0.f, wdb = 0.f;
+#pragma unroll
+                            for (int kk = 0; kk < kMaxDim; ++kk) { if (kk == da) wda = wx[kk]; if (kk == db) wdb = wx[kk]; }
+                            if (k == da) G[k] = fmaf(A[c], wdb, G[k]);
+                            if (k == db) G[k] = fmaf(A[c], wda, G[k]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k)
+                if (k < args.dim) atomicAdd(args.g_wx + (int64_t)g * args.g_wx_ld + k, G[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxDim; ++k) G[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) A[c] = 0.f;
+    };
+    auto load_feature_constants = [&](int f0) {
+        flush_sums();
+        cur_f0 = f0;
+        const int fw = f0 + quarter * 32;
+        g = fw + lane;
+        g_ok = g < args.n_feat;
+        live = fw < args.n_store && has_blocks;
+        if constexpr (kBwd0) {
+#pragma unroll
+            for (int k = 0; k < kMaxDim; ++k) wx[k] = (k < args.dim && g_ok) ? __ldg(args.Wx + g * args.dim + k) : 0.f;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                float wa = 1.f, wb = 1.f;
+#pragma unroll
+                for (int k = 0; k < kMaxDim; ++k) {
+                    if (spec.kind[c] == 1 && k == spec.dir[c]) wa = wx[k];
+                    if (spec.kind[c] == 2 && k == spec.dir[spec.pa[c]]) wa = wx[k];
+                    if (spec.kind[c] == 2 && k == spec.dir[spec.pb[c]]) wb = wx[k];
+                }
+                cf[c] = wa * wb;
+            }
+        }
+    };
+
+    // ---- item sequence (tile it, 8-row block rb) and the prefetch pipeline, as in fwd_epilogue_loop ----
+    struct Item { int it, rb, f0, r0; bool ok; };
+    auto next_item = [&](const Item& c) {
+        Item n = c;
+        if (has_blocks && c.rb + EPI_PQ < NRB) { n.rb = c.rb + EPI_PQ; return n; }
+        n.it = c.it + 1;
+        n.rb = sub;
+        n.ok = tile(n.it, n.f0, n.r0);
+        return n;
+    };
+    auto load_rows = [&](const Item& m, float& xv, int& vv) {
+        const int rr = min(m.r0 + m.rb * 8 + (lane & 7), args.rows - 1);
+        xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
+        vv = __ldg(args.vtx + rr);
+    };
+    auto store_rows = [&](int slot, float xv, int vv) {
+        const uint32_t a = row_addr + slot * kSlot;
+        sts_f32(a + (lane & 7) * 16 + (lane >> 3) * 4, xv);
+        if (lane < 8) sts_f32(a + 128 + lane * 4, __int_as_float(vv));
+    };
+    auto gather_vb = [&](const Item& m, int slot, float* zraw) {       // MODE 3: Vb[vertex] of the item's 8 rows
+        const int gm = m.f0 + quarter * 32 + lane;
+        const bool ok = gm < args.n_feat;
+        const float* vb = args.Vb + args.cat_off + (ok ? gm : 0);
+        const uint32_t a = row_addr + slot * kSlot + 128;
+        static_for<8>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const int vt = (int)lds_b32(a + i * 4);
+            zraw[i] = ok ? __ldg(vb + (int64_t)vt * args.ncat) : 0.f;
+        });
+    };
+    // MODE 2: the z planes stream from HBM (no reuse): pull the lines of an item into L2 ahead of time, one 128-byte
+    // line (32 features of one row and component) per lane
+    auto prefetch_z = [&](const Item& m) {
+        const int gm0 = m.f0 + quarter * 32;
+        if (gm0 < args.n_feat) {
+            for (int idx = lane; idx < KC * 8; idx += 32) {
+                const int rn = min(m.r0 + m.rb * 8 + (idx & 7), args.rows - 1);
+                prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + gm0);
+            }
+        }
+    };
+
+    Item cur{0, sub, 0, 0, false};
+    cur.ok = tile(0, cur.f0, cur.r0);
+    if (!cur.ok) return;
+    if (!has_blocks) {
+        for (int it = 0; cur.ok; ++it, cur.ok = tile(it, cur.f0, cur.r0)) {
+            mbar_wait(tfull_addr0 + (it & 1) * 8, (it >> 1) & 1, args.status, args.wait_ns);
+            hand_back(it & 1);
+        }
+        return;
+    }
+    float zn[kBwd0 ? 8 : 1], zs[kBwd0 ? 8 : 1];
+    {
+        float xv; int vv;
+        load_rows(cur, xv, vv);
+        store_rows(0, xv, vv);
+    }
+    Item nxt = next_item(cur);
+    {
+        float xv = 0.f; int vv = 0;
+        if (nxt.ok) load_rows(nxt, xv, vv);
+        store_rows(1, xv, vv);
+    }
+    __syncwarp();
+    if constexpr (kBwd0) gather_vb(cur, 0, zn);
+    float amax = 0.f;
+    int slot = 0;
+
+    while (cur.ok) {
+        if (cur.f0 != cur_f0) load_feature_constants(cur.f0);
+        const uint32_t rs = row_addr + slot * kSlot;
+        if constexpr (kBwd0) {                                   // z_0 of layer 0 for the 8 rows (gather issued an item ago)
+            static_for<8>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                const uint4 x = lds_v4(rs + i * 16);
+                float z = zn[i];
+                z = fmaf(wx[0], __uint_as_float(x.x), z);
+                z = fmaf(wx[1], __uint_as_float(x.y), z);
+                z = fmaf(wx[2], __uint_as_float(x.z), z);
+                z = fmaf(wx[3], __uint_as_float(x.w), z);
+                zs[i] = z;
+            });
+        }
+        float xv2 = 0.f; int vv2 = 0;
+        if (nxt.ok) {
+            if constexpr (kBwd0) gather_vb(nxt, slot ^ 1, zn);
+            else prefetch_z(nxt);
+            const Item nn = next_item(nxt);
+            if (nn.ok) load_rows(nn, xv2, vv2);
+        }
+        const int buf = cur.it & 1;
+        const uint32_t taddr = tmem_q + buf * n_cols;
+        const bool first_of_tile = cur.rb == sub;
+        const bool last_of_tile = !(cur.rb + EPI_PQ < NRB);
+        if (first_of_tile) {
+            mbar_wait(tfull_addr0 + buf * 8, (cur.it >> 1) & 1, args.status, args.wait_ns);
+            tc_fence_after();
+        }
+        if (!live) {
+            if (last_of_tile) hand_back(buf);
+        } else {
+        const int rbase = cur.r0 + cur.rb * 8;
+        const int fw = cur.f0 + quarter * 32;
+        const float* zbase = kBwd0 ? nullptr : args.z_in + (int64_t)rbase * args.ldz + (g_ok ? g : 0);
+        dispatch_act(args.act, [&](auto act_c) {
+        constexpr int kAct = decltype(act_c)::value;
+        static_for<NPASS>([&](auto PS) {
+            constexpr int ps = decltype(PS)::value;
+            const uint32_t sl = stg_addr + lane * 2;
+            static_for<CHUNKS>([&](auto CH) {
+                constexpr int ch = decltype(CH)::value;
+                constexpr int i0 = (kBwd0 ? 0 : ps * SR) + ch * TL;       // first row of the chunk inside the 8-row block
+                uint32_t v[KC][TL];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) tmem_ld_n<TL>(taddr + cur.rb * (8 * KC) + c * 8 + i0, v[c]);
+                float zc[kBwd0 ? 1 : KC][TL];
+                if constexpr (!kBwd0) {
+#pragma unroll
+                    for (int c = 0; c < KC; ++c)
+#pragma unroll
+                        for (int j = 0; j < TL; ++j) {
+                            const int rr = min(rbase + i0 + j, args.rows - 1) - rbase;
+                            zc[c][j] = g_ok ? __ldg(zbase + (int64_t)c * zplane + (int64_t)rr * args.ldz) : 0.f;
+                        }
+                }
+                tmem_wait_ld();
+                if (ps == NPASS - 1 && ch == CHUNKS - 1 && last_of_tile) hand_back(buf);
+                static_for<TL>([&](auto JT) {
+                    constexpr int j = decltype(JT)::value;
+                    constexpr int i = i0 + j;
+                    constexpr int ir = i - ps * SR;                    // row inside the staging pass (MODE 2)
+                    const int r = rbase + i;
+                    const bool r_ok = r < args.rows;
+                    const uint4 x = lds_v4(rs + i * 16);
+                    const float xr[kMaxDim] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+                    const int vrow = (int)lds_b32(rs + 128 + i * 4);
+                    float ab[KC];
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) ab[c] = (g_ok && r_ok) ? __uint_as_float(v[c][j]) * scale : 0.f;
+                    const float z0 = kBwd0 ? zs[kBwd0 ? i : 0] : zc[0][j];
+                    float s1, s2, s3, z0b;
+                    act_d123_fast(kAct, args.beta, z0, s1, s2, s3);
+                    if constexpr (!kBwd0) {
+                        float zb[KC];
+                        float u = 0.f, w3 = 0.f;
+                        if constexpr (SPEC == kSpecRb2 && KC == 6) {
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) { u = fmaf(ab[c], zc[c][j], u); zb[c] = s1 * ab[c]; }
+                            const float p4 = ab[4] * zc[2][j], p5 = ab[5] * zc[3][j];
+                            w3 = fmaf(p4, zc[2][j], p5 * zc[3][j]);
+                            zb[2] = fmaf(2.f * s2, p4, zb[2]);
+                            zb[3] = fmaf(2.f * s2, p5, zb[3]);
+                        } else {
+                            float cross[STPDE_MAX_FIRST];
+#pragma unroll
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k) cross[k] = 0.f;
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) {
+                                u = fmaf(ab[c], zc[c][j], u);
+                                zb[c] = s1 * ab[c];
+                                if (c > n_first) {                 // second order (warp-uniform): parents za, zp
+                                    float za = 0.f, zp = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k) {
+                                        if (1 + k < KC) {
+                                            za = fmaf(spec.sel_a[c][k], zc[1 + k][j], za);
+                                            zp = fmaf(spec.sel_b[c][k], zc[1 + k][j], zp);
+                                        }
+                                    }
+                                    w3 = fmaf(ab[c] * za, zp, w3);
+#pragma unroll
+                                    for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                        if (1 + k < KC) cross[k] = fmaf(ab[c], fmaf(spec.sel_a[c][k], zp, spec.sel_b[c][k] * za), cross[k]);
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < STPDE_MAX_FIRST; ++k)
+                                if (1 + k < KC) zb[1 + k] = fmaf(s2, cross[k], zb[1 + k]);
+                        }
+                        z0b = fmaf(s1, ab[0], fmaf(s2, u, s3 * w3));
+                        zb[0] = z0b;
+                        if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
+                            float sb0, sb1, sb2;
+                            swish_dbeta(args.beta, z0, sb0, sb1, sb2);
+                            bsum += fmaf(ab[0], sb0, fmaf(sb1, u, sb2 * w3));
+                        }
+#pragma unroll
+                        for (int c = 1; c < KC; ++c) A[c] += zb[c];
+                        if constexpr (ir == 0) {                   // the TMA engine has read the buffer's previous contents
+                            if (lane == 0) bulk_wait_read0();
+                            __syncwarp();
+                        }
+                        static_for<KC>([&](auto C) {
+                            constexpr int c = decltype(C)::value;
+                            const float xs = zb[c];
+                            amax = fmaxf(amax, fabsf(xs));
+                            const __half hi = __float2half_rn(xs);
+                            sts_b16_o<(c * SR + ir) * 64>(sl, hi);
+                            if constexpr (OUTK == 0)
+                                sts_b16_o<(KC * SR + c * SR + ir) * 64>(sl, __float2half_rn(xs - __half2float(hi)));
+                        });
+                    } else {
+                        // layer 0: a_c = sigma^(order_c)(z0) * cf_c
+                        float t1 = 0.f, t2 = 0.f;
+                        if constexpr (SPEC == kSpecRb2 && KC == 6) {
+                            t1 = fmaf(ab[1], cf[1], fmaf(ab[2], cf[2], ab[3] * cf[3]));
+                            t2 = fmaf(ab[4], cf[4], ab[5] * cf[5]);
+#pragma unroll
+                            for (int c = 1; c < 4; ++c) A[c] = fmaf(ab[c], s1, A[c]);
+                            A[4] = fmaf(ab[4], s2, A[4]);
+                            A[5] = fmaf(ab[5], s2, A[5]);
+                        } else {
+#pragma unroll
+                            for (int c = 1; c < KC; ++c) {
+                                const float pc = ab[c] * cf[c];
+                                if (c <= n_first) { t1 += pc; A[c] = fmaf(ab[c], s1, A[c]); }
+                                else { t2 += pc; A[c] = fmaf(ab[c], s2, A[c]); }
+                            }
+                        }
+                        z0b = fmaf(s1, ab[0], fmaf(s2, t1, s3 * t2));
+                        if (kAct == STPDE_ACT_SWISH && swish_beta_rt) {
+                            float sb0, sb1, sb2;
+                            swish_dbeta(args.beta, z0, sb0, sb1, sb2);
+                            bsum += fmaf(ab[0], sb0, fmaf(sb1, t1, sb2 * t2));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
+                    if (g_ok && r_ok) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+                });
+            });
+            if constexpr (!kBwd0) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&args.out_map[0], stg_addr, fw, rbase + ps * SR, 0);
+                    if constexpr (OUTK == 0) tma_store_3d(&args.out_map[1], stg_addr + KC * SR * 64, fw, rbase + ps * SR, 0);
+                    bulk_commit();
+                }
+            }
+        });
+        });
+        }
+        __syncwarp();
+        store_rows(slot, xv2, vv2);
+        __syncwarp();
+        slot ^= 1;
+        cur = nxt;
+        if (cur.ok) nxt = next_item(cur);
+    }
+    flush_sums();
+    if (swish_beta_rt) {
+        for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+        if (lane == 0) atomicAdd(args.g_beta, bsum);
+    }
+    if (!(amax < 65000.f)) atomicOr(args.status, kStatusRange);
+    if (!kBwd0 && lane == 0) bulk_wait0();
+}
+
+template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class TileFn, class HandBack>
+__device__ __forceinline__ void bwd_epilogue(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
+                                             int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
+                                             uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
+    if (MODE == kModeBwd0 || args.passes == 3)
+        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+    else
+        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+}
+
 // bytes of output staging a kernel mode needs (all 16 epilogue warps); the reverse modes still store directly
 template <int KC, int MODE, bool SINGLE = false>
 __host__ __device__ constexpr uint32_t epi_staging_total() {
-    return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + (SINGLE ? kRowScratchFused : kRowScratch)) : 0u;
+    return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + (SINGLE ? kRowScratchFused : kRowScratch))
+           : MODE == kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes_bwd(KC) + kRowScratch)
+                              : (uint32_t)kEpiWarps * kRowScratch;           // MODE 3 writes no planes
 }
 
 template <int KC, int SPEC = 0, int MODE = kModeFwd>
@@ -1082,17 +1198,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         };
         if constexpr (MODE >= kModeBwd) {
-            int it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-                const int tn = t + gridDim.x;
-                const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF + quarter * 32 : -1;
-                const int next_r0 = (tn / n_ftiles) * NR;
-                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, tmem_q + buf * N,
-                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
-                hand_back(buf);
-            }
+            auto tile = [&](int it, int& f0, int& r0) {
+                const int t = blockIdx.x + it * gridDim.x;
+                f0 = (t % n_ftiles) * kTileF;
+                r0 = (t / n_ftiles) * NR;
+                return t < n_tiles;
+            };
+            constexpr uint32_t kStg = MODE == kModeBwd ? epi_stage_bytes_bwd(KC) : 0u;
+            bwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * kStg,
+                                                              smem_u32(staging) + kEpiWarps * kStg + (warp - 2) * kRowScratch,
+                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         } else {
             auto tile = [&](int it, int& f0, int& r0) {
                 const int t = blockIdx.x + it * gridDim.x;
@@ -1144,13 +1259,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Same without release semantics, for the reverse-mode epilogue only: it hands the accumulator back AFTER the tile's
-// global stores / reds were issued, and the releasing form would drain them first (MEMBAR.ALL.GPU + ERRBAR, ~8 % of
-// that epilogue's stall samples).  Its tcgen05.ld results are in registers (tcgen05.wait::ld +
-// tcgen05.fence::before_thread_sync) long before the arrive; the forward epilogue uses the release form.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t leader_bar) {
     asm volatile(
@@ -1311,36 +1419,27 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
         const uint32_t tmem_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t tempty_leader0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_cta(smem_u32(&tempty_bar[1]), 0);
+        // TMEM hand-back to the leader's barrier: the tcgen05.ld results are in registers (tcgen05.wait::ld +
+        // tcgen05.fence::before_thread_sync) and the arrive carries the default .release.cta semantics - the
+        // cluster-scope release measured 20 % of this warp's stall samples (MEMBAR + ERRBAR drain every outstanding
+        // global access, including the prefetches issued on purpose just before).
+        auto hand_back = [&](int buf) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);
+        };
+        auto tile = [&](int it, int& f0, int& r0) {
+            const int t = pair_id + it * n_pairs;
+            f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF;
+            r0 = (t / n_ftiles) * NR;
+            return t < n_tiles;
+        };
         if constexpr (MODE >= kModeBwd) {
-            int it = 0;
-            for (int t = pair_id; t < n_tiles; t += n_pairs, ++it) {
-                const int buf = it & 1;
-                const int f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF, r0 = (t / n_ftiles) * NR;
-                const int tn = t + n_pairs;
-                const int next_f0 = tn < n_tiles ? (tn % n_ftiles) * kTileF2 + (int)rank * kTileF + quarter * 32 : -1;
-                const int next_r0 = (tn / n_ftiles) * NR;
-                bwd_epilogue_tile<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, f0, r0, quarter, sub, lane, tmem_q + buf * N,
-                                                                       smem_u32(&tfull_bar[buf]), (it >> 1) & 1, next_f0, next_r0);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
-            }
+            constexpr uint32_t kStg = MODE == kModeBwd ? epi_stage_bytes_bwd(KC) : 0u;
+            bwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * kStg,
+                                                              smem_u32(staging) + kEpiWarps * kStg + (warp - 2) * kRowScratch,
+                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         } else {
-            // TMEM hand-back to the leader's barrier: the tcgen05.ld results are in registers (tcgen05.wait::ld +
-            // tcgen05.fence::before_thread_sync) and the arrive carries the default .release.cta semantics - the
-            // cluster-scope release measured 20 % of this warp's stall samples (MEMBAR + ERRBAR drain every outstanding
-            // global access, including the prefetches issued on purpose just before).
-            auto hand_back = [&](int buf) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);
-            };
-            auto tile = [&](int it, int& f0, int& r0) {
-                const int t = pair_id + it * n_pairs;
-                f0 = (t % n_ftiles) * kTileF2 + (int)rank * kTileF;
-                r0 = (t / n_ftiles) * NR;
-                return t < n_tiles;
-            };
             fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, false>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
                                                               smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratch,
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);

@@ -56,7 +56,7 @@ static inline bool spec_is_rb2(const JetSpec& s) {
 }
 
 // Fills a.out_map for the output planes of a forward layer launch (tc_path.cu).
-int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32);
+int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32, bool reverse = false);
 
 #ifdef STPDE_TC_LAUNCH_IMPL
 template <int KC, int SPEC = 0>

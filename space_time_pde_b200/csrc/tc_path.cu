@@ -256,12 +256,12 @@ const TcEnv& tc_env() {
 
 // TMA store maps of a layer's output planes [kc][rows][ld_out]: box = 32 features x stage_rows(kc) rows x kc components,
 // no swizzle (the epilogue warps write their staging buffers in exactly that order).
-int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32) {
+int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32, bool reverse) {
     cuuint64_t dims[3] = {(cuuint64_t)a.ld_out, (cuuint64_t)a.rows, (cuuint64_t)kc};
     const size_t es = f32 ? sizeof(float) : sizeof(__half);
     cuuint64_t strides[2] = {(cuuint64_t)a.ld_out * es, (cuuint64_t)a.ld_out * a.rows * es};
     // rows per store: stage_rows(kc), twice that when only one fp16 plane is written (same staging bytes)
-    const int srb = tc::stage_rows(kc);
+    const int srb = reverse ? tc::stage_rows_bwd(kc) : tc::stage_rows(kc);
     const int box_rows = (!f32 && !plane1 && srb < 8) ? 2 * srb : srb;
     cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)kc};
     cuuint32_t estr[3] = {1, 1, 1};

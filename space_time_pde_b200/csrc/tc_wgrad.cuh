@@ -204,7 +204,7 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(buf ? tempty_leader1 : tempty_leader0);
+            if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);
         }
     }
     tc_fence_before();
