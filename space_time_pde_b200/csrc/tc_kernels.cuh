@@ -56,8 +56,8 @@ __host__ __device__ constexpr int stage_rows_base(int kc) {
 __host__ __device__ constexpr int stage_rows(int kc) {
     return stage_rows_base(kc) / STPDE_EPI_SR_DIV > 0 ? stage_rows_base(kc) / STPDE_EPI_SR_DIV : 1;
 }
-// reverse mode: the rows of a staging pass must cover one TMEM chunk (2 rows for K > 3)
-__host__ __device__ constexpr int stage_rows_bwd(int kc) { return stage_rows(kc) < 2 && kc > 3 ? 2 : stage_rows(kc); }
+// reverse mode: same staging granularity (a TMEM chunk never spans two staging passes: TL = min(rows per chunk, SR))
+__host__ __device__ constexpr int stage_rows_bwd(int kc) { return stage_rows(kc); }
 __host__ __device__ constexpr uint32_t epi_stage_bytes_bwd(int kc) { return (uint32_t)kc * stage_rows_bwd(kc) * 128u; }
 __host__ __device__ constexpr uint32_t epi_stage_bytes(int kc) {
     return (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;

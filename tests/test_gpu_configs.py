@@ -170,3 +170,51 @@ def test_setup_cache_for_inference_loops(dev):
     grid = grid * 1.0                                            # a new tensor (new storage): setup runs again
     _, _, n5 = run(q)
     assert n5 > 0
+
+
+def test_evaluation_grid_pattern_at_size(dev):
+    """SURVEY 8(f) rank 3 - the query pattern of experiments/rb2d/evaluation.py:46-74,222-240 at its real size, in ONE call:
+    a structured linspace(eps, max - eps) grid of 192 x 128 x 512 = 12.6 M points (its first / last planes sit exactly on
+    the clip bounds: tie points), tensor bounds maxs = [t_max, 1, 4] on the device, a stride-0 expanded batch and a
+    permuted (non-contiguous) latent grid.  A slice that contains tie points, interior points and the far corner is
+    checked against the fp64 oracle; the 10 000-point pseudo-batch loop of the reference must give the same numbers."""
+    torch.manual_seed(31)
+    nt, nz, nx, nf = 192, 128, 512, 32
+    model = sp.ImNet(dim=3, in_features=32, out_features=4, nf=nf, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    latent = (torch.randn(1, 32, nt // 4, nz // 8, nx // 8, device=dev) * 0.5).permute(0, 2, 3, 4, 1)
+    assert not latent.is_contiguous()
+    t_max, eps = nt / 16.0, 1e-6
+    mins = torch.zeros(3, dtype=torch.float32, device=dev)
+    maxs = torch.tensor([t_max, 1.0, 4.0], dtype=torch.float32, device=dev)
+    seqs = [torch.linspace(eps, m - eps, n) for m, n in zip((t_max, 1.0, 4.0), (nt, nz, nx))]
+    coord = torch.stack(torch.meshgrid(*seqs, indexing="ij"), dim=-1).reshape(-1, 3).to(dev)
+    n_query = coord.shape[0]
+    layer = sp.get_rb2_pde_layer(t_crop=t_max, z_crop=1., x_crop=4., prandtl=1., rayleigh=1e6, use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, latent, pts, mins, maxs))
+    batch = coord[None].expand(1, n_query, 3)
+    assert batch.stride(0) == 0 or batch.shape[0] == 1
+    with torch.no_grad():
+        y, res = layer(batch, return_residue=True)
+    assert y.shape == (1, n_query, 4) and all(v.shape == (1, n_query, 1) for v in res.values())
+    assert torch.isfinite(y).all() and all(torch.isfinite(v).all() for v in res.values())
+    # slice: the first z-x plane rows (t = eps: tie points on the lower clip bound), an interior block, the last points
+    idx = torch.cat([torch.arange(0, 96), torch.arange(n_query // 2 + 12345, n_query // 2 + 12345 + 96),
+                     torch.arange(n_query - 64, n_query)]).to(dev)
+    Ws = [l.weight.detach().cpu().numpy() for l in model.fc]
+    bs = [l.bias.detach().cpu().numpy() for l in model.fc]
+    qn = coord[idx][None].cpu().numpy()
+    xmax = maxs.cpu().numpy()
+    yj = jo.query_jet(latent.cpu().numpy(), qn, np.zeros(3, np.float32), xmax, Ws, bs, "softplus")
+    iv, ov, eqs = jo.rb2_equations(t_crop=t_max, z_crop=1., x_crop=4., prandtl=1., rayleigh=1e6, use_continuity=True)
+    ref = jo.pde_residuals(yj, qn, iv, ov, eqs)
+    assert record("eval_grid", "y", rel_linf(y[:, idx].cpu().numpy(), yj.v), 1e-5) < 1e-5
+    for k, v in res.items():
+        # tie points: the reference's own float32 run is 2e-3 away from float64 there (fixture rb2_ties_softplus);
+        # this path follows the float64 values
+        assert record("eval_grid", k, rel_linf(v[:, idx].cpu().numpy(), ref[k]), 1e-5) < 1e-5, k
+    # the reference's pseudo-batch loop over the same points (evaluation.py:54-69): identical numbers
+    with torch.no_grad():
+        for s0 in (0, 5 * 10_000, n_query - 10_000):
+            yb, rb = layer(coord[s0:s0 + 10_000][None].expand(1, 10_000, 3), return_residue=True)
+            assert torch.equal(yb, y[:, s0:s0 + 10_000])
+            assert all(torch.equal(rb[k], res[k][:, s0:s0 + 10_000]) for k in rb)
