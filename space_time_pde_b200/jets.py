@@ -24,6 +24,49 @@ _test_backend = None          # tests only: CPU stand-in for the kernel (see _to
 DEFAULT_PRECISION = os.environ.get("STPDE_PRECISION", "fp16x3")
 
 
+# STPDE_ASYNC=1 keeps the host from waiting for every call's status word.  The word is copied to pinned host memory behind
+# the call instead, and every later call (or ``check_pending()``) raises for the calls that have finished since - errors
+# are delayed, never dropped.
+_pending: list = []
+
+
+def _raise_for_status(flags: int, where: str) -> None:
+    if flags & 1:
+        raise IndexError("query point addressed a cell outside the latent grid "
+                         "(reference regular_nd_grid_interpolation.py:52 ignores xmin; use xmin = 0)" + where)
+    if flags & 2:
+        if "backward" in where:
+            raise _lib.StpdeError(-6, "an adjoint left the fp16 range of the split-precision tensor-core backward; "
+                                      "set STPDE_BACKWARD=torch to use the autograd re-evaluation" + where)
+        raise _lib.StpdeError(-6, "activation left the fp16 range of the split-precision tensor-core path; "
+                                  "use precision='fp32'" + where)
+
+
+def _defer_status(status: torch.Tensor, where: str) -> None:
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(status.device))
+    _pending.append((ev, host, where))
+
+
+def check_pending(wait: bool = False) -> None:
+    """Raise for every asynchronous call whose status word has arrived (``wait=True``: synchronise on all of them)."""
+    keep = []
+    err = None
+    for ev, host, where in _pending:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            if err is None and int(host[0]) & 3:
+                err = (int(host[0]), where)
+        else:
+            keep.append((ev, host, where))
+    _pending[:] = keep
+    if err is not None:
+        _raise_for_status(err[0], f" [reported late: {err[1]} call under STPDE_ASYNC=1]")
+
+
 def set_test_backend(fn) -> None:
     """Install a stand-in jet provider (tests of the host logic on machines without a GPU)."""
     global _test_backend
@@ -84,22 +127,29 @@ def active_request() -> Optional[JetRequest]:
 # ----------------------------------------------------------------------------------------------
 # workspace cache (one growing byte buffer per device; the C ABI never allocates)
 # ----------------------------------------------------------------------------------------------
-_workspaces: Dict[torch.device, torch.Tensor] = {}
+def _slot(device: torch.device):
+    """Scratch is owned per (device, CUDA stream): two streams of one device may have calls in flight at the same time,
+    and a call's scratch (workspace, training stash) is only ordered on the stream it was launched on."""
+    return (device, torch.cuda.current_stream(device).cuda_stream) if device.type == "cuda" else (device, 0)
+
+
+_workspaces: Dict[tuple, torch.Tensor] = {}
 # What the call-invariant region of a device's workspace currently holds (packed / split weights, per-vertex table):
 # identity + version of the latent grid and of every decoder parameter, shapes, precision.  An inference call that finds
 # its own key here skips the per-call setup kernels (desc.reserved[1] = 1) - evaluation loops decode thousands of
 # pseudo-batches against the same grid and weights (reference experiments/rb2d/evaluation.py:54-69).
 # STPDE_SETUP_CACHE=0 disables it (in-place edits through ``.data`` do not bump tensor versions).
-_setup_keys: Dict[torch.device, tuple] = {}
+_setup_keys: Dict[tuple, tuple] = {}
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _workspaces.get(device)
+    key = _slot(device)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        _workspaces.pop(device, None)
+        _workspaces.pop(key, None)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
-        _setup_keys.pop(device, None)
+        _workspaces[key] = ws
+        _setup_keys.pop(key, None)
     return ws
 
 
@@ -121,16 +171,17 @@ class _Stash:
         self.precision = ""      # arithmetic of the forward that filled it (a single-pass forward leaves no lo planes)
 
 
-_stashes: Dict[torch.device, _Stash] = {}
+_stashes: Dict[tuple, _Stash] = {}
 _stash_tokens = itertools.count(1)
 
 
 def _stash(device: torch.device, nbytes: int) -> _Stash:
-    st = _stashes.get(device)
+    key = _slot(device)
+    st = _stashes.get(key)
     if st is None or st.ws.numel() < nbytes:
-        _stashes.pop(device, None)
+        _stashes.pop(key, None)
         st = _Stash(torch.empty(nbytes, dtype=torch.uint8, device=device))
-        _stashes[device] = st
+        _stashes[key] = st
     return st
 
 
@@ -245,8 +296,8 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
                 key = (ws.data_ptr(), grid.data_ptr(), grid._version, tuple(grid.shape), tuple(grid.stride()),
                        tuple((w.data_ptr(), w._version) for w in list(Wc) + list(Bc)), tuple(widths), act, float(act_param),
                        precision, tuple(float(v) for v in lo), tuple(float(v) for v in hi))
-            desc.reserved[1] = 1 if (key is not None and _setup_keys.get(device) == key) else 0
-            _setup_keys[device] = key
+            desc.reserved[1] = 1 if (key is not None and _setup_keys.get(_slot(device)) == key) else 0
+            _setup_keys[_slot(device)] = key
             rc = lib.stpde_jet_forward(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr, bptr,
                                        y.data_ptr(), sub_jets.data_ptr() if sub_jets is not None else None,
                                        ws.data_ptr(), ws.numel(), status.data_ptr(), stream)
@@ -256,14 +307,12 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
                 jets[:nf] = sub_jets[:nf]
                 for i, pair in enumerate(sub.second):
                     jets[nf + spec.second.index(pair)] = sub_jets[nf + i]
-    if check and os.environ.get("STPDE_ASYNC", "0") != "1":
-        flags = int(status.item())
-        if flags & 1:
-            raise IndexError("query point addressed a cell outside the latent grid "
-                             "(reference regular_nd_grid_interpolation.py:52 ignores xmin; use xmin = 0)")
-        if flags & 2:
-            raise _lib.StpdeError(-6, "activation left the fp16 range of the split-precision tensor-core path; "
-                                      "use precision='fp32'")
+    if check:
+        if os.environ.get("STPDE_ASYNC", "0") != "1":
+            _raise_for_status(int(status.item()), "")
+        else:
+            check_pending()
+            _defer_status(status, "forward")
     return y, jets
 
 
@@ -306,12 +355,12 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
         nbytes = lib.stpde_backward_workspace_bytes(ctypes.byref(desc))
         if nbytes == 0:
             raise _lib.StpdeError(-1, lib.stpde_last_error().decode())
-        st = _stashes.get(device)
+        st = _stashes.get(_slot(device))
         reuse = 1 if (stash_token and st is not None and st.token == stash_token and st.ws.numel() >= nbytes
                       and (precision == "fp16" or st.precision != "fp16")) else 0
         ws = st.ws if reuse else _workspace(device, nbytes)
         if not reuse:
-            _setup_keys.pop(device, None)          # the shared workspace is about to be overwritten
+            _setup_keys.pop(_slot(device), None)   # the shared workspace is about to be overwritten
         # The adjoints travel through fp16 hi/lo planes behind a power-of-two scale; if one overflows (status bit 1)
         # the sweep is repeated with 6 more bits of headroom.
         for headroom in (0, 6, 12, 24):
@@ -322,11 +371,17 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
                                         ggrid.data_ptr() if ggrid is not None else None, gbeta.data_ptr(),
                                         ws.data_ptr(), ws.numel(), reuse, status.data_ptr(), stream)
             _lib.check(rc)
-            if not sync or not (int(status.item()) & 2):
+            if not sync:
+                # asynchronous mode: no retry with more headroom is possible without reading the flag back; the
+                # overflow is reported by a later call instead of being dropped
+                if check:
+                    check_pending()
+                    _defer_status(status, "backward")
+                break
+            if not (int(status.item()) & 2):
                 break
         else:
-            raise _lib.StpdeError(-6, "an adjoint left the fp16 range of the split-precision tensor-core backward; "
-                                      "set STPDE_BACKWARD=torch to use the autograd re-evaluation")
+            _raise_for_status(2, " (backward, after 4 retries with more headroom)")
     return ggrid, gW, gB, gbeta
 
 

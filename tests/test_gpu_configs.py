@@ -218,3 +218,22 @@ def test_evaluation_grid_pattern_at_size(dev):
             yb, rb = layer(coord[s0:s0 + 10_000][None].expand(1, 10_000, 3), return_residue=True)
             assert torch.equal(yb, y[:, s0:s0 + 10_000])
             assert all(torch.equal(rb[k], res[k][:, s0:s0 + 10_000]) for k in rb)
+
+
+def test_async_mode_reports_errors_late_but_never_drops_them(dev, monkeypatch):
+    """STPDE_ASYNC=1: no host wait per call; the status word of a call is read back behind it and raised by a later call or
+    by jets.check_pending(wait=True) (the asynchronous mode used to skip the checks altogether)."""
+    monkeypatch.setenv("STPDE_ASYNC", "1")
+    torch.manual_seed(12)
+    model = sp.ImNet(dim=3, in_features=8, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 3, 4, 5, 8, device=dev) * 0.5
+    q = torch.rand(1, 500, 3, device=dev)
+    jets.check_pending(wait=True)
+    with torch.no_grad():
+        y = sp.query_local_implicit_grid(model, grid, q, 0., 1.)                 # fine
+        jets.check_pending(wait=True)
+        y_bad = sp.query_local_implicit_grid(model, grid, q + 2.0, 2., 3.)       # walks off the grid (quirk Q1): no raise yet
+    with pytest.raises(IndexError):
+        jets.check_pending(wait=True)
+    jets.check_pending(wait=True)                                                # reported once
+    assert torch.isfinite(y).all() and y_bad.shape == y.shape
