@@ -392,7 +392,15 @@ def leg_config3(ctx, args, peaks):
         out["means"] = reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": n_glob / world, "pde": n_glob / world})
 
     try:
-        ms = ctx.time(step, 1, 1)
+        from space_time_pde_b200 import _lib
+        lib = _lib.load()
+        step()                                                    # warm-up
+        ctx.barrier()
+        lib.stpde_profile_enable(1)
+        _lib.profile_read()
+        ms = ctx.time(step, 1, 0)
+        prof = _lib.profile_read()
+        lib.stpde_profile_enable(0)
         with torch.no_grad():
             y, res = layer(q[:1, :512], return_residue=True)
         par = oracle_parity(model, grid, q, y, res, 256, rb2_kwargs=rb2)
@@ -406,6 +414,8 @@ def leg_config3(ctx, args, peaks):
                 "points_per_rank": B * p_rank, "chunk_points": B * chunk,
                 "roofline": roofline_of(rate / world, fpt, peaks, 1, mult=3.0),
                 "parity": dict(par, mode="relaxed 16-bit mode: forward values + residuals vs fp64 oracle"),
+                "kernel_ms_per_step": {k: round(v[0], 2) for k, v in prof.items() if v[1] > 0},
+                "gpu_launches_per_step": int(sum(v[1] for v in prof.values())),
                 "loss_reg": float(out["means"]["reg"]), "loss_pde": float(out["means"]["pde"])}
     finally:
         for p_ in params:
@@ -661,7 +671,7 @@ def main():
                     help="timed training steps (forward + residuals + loss + fused backward [+ all-reduce]); 0 skips the leg")
     ap.add_argument("--legs", default="config2_train,config3,config4,config5,eval_grid",
                     help="comma-separated optional legs ('' = headline only)")
-    ap.add_argument("--config3-chunk", type=int, default=131072, help="points (all crops) per chunk of the config-3 step")
+    ap.add_argument("--config3-chunk", type=int, default=65536, help="points (all crops) per chunk of the config-3 step")
     ap.add_argument("--config4-points", type=int, default=1 << 20, help="query points per GPU of the config-4 leg (of 4 M)")
     ap.add_argument("--config5-points", type=lambda s: [int(float(x)) for x in s.split(",")], default=[10_000, 1_000_000, 64_000_000])
     ap.add_argument("--eval-grid", type=lambda s: tuple(int(x) for x in s.split("x")), default=(192, 128, 512))

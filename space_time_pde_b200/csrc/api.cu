@@ -192,6 +192,8 @@ static int64_t default_chunk_points(const Plan& P) {
     return pc;
 }
 
+static int64_t balanced_chunk_points(int64_t total_pts, int64_t pc_max);
+
 static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, const float* q,
                        const float* const* W, const float* const* B, float* y, float* jets, char* ws,
                        size_t ws_bytes, int* status, cudaStream_t st) {
@@ -202,6 +204,7 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     int64_t need = (P.total_pts + 127) / 128 * 128;
     if (pc > need) pc = need;
     if (pc > (1 << 24)) pc = 1 << 24;
+    pc = balanced_chunk_points(P.total_pts, pc);
     const int dim = d->dim, kc = P.spec.kc;
     const int64_t rows = pc * P.ncorner;
     if (rows * (int64_t)(P.max_even > P.max_odd ? P.max_even : P.max_odd) * kc >= (int64_t)1 << 40)
@@ -310,6 +313,16 @@ static int run_forward(const Plan& P, const stpde_desc_t* d, const float* grid, 
     return STPDE_OK;
 }
 
+// Every chunk runs the kernels over the full chunk geometry, so a short last chunk wastes the difference (and its padding
+// rows all address vertex 0: their zero-valued adjoint atomics serialise on one table row - measured 4x on a 122k + 9k
+// split).  Split the call into equal chunks instead: same count, each at most pc_max points.
+static int64_t balanced_chunk_points(int64_t total_pts, int64_t pc_max) {
+    if (pc_max < 128 || total_pts <= pc_max) return pc_max;
+    const int64_t n_chunks = (total_pts + pc_max - 1) / pc_max;
+    const int64_t pc = ((total_pts + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    return pc < pc_max ? pc : pc_max;
+}
+
 static size_t bwd_chunk_region_bytes(const Plan& P, int64_t pc) { return (size_t)pc * P.bwd_per_point_bytes + 64 * 1024; }
 
 static int64_t default_bwd_chunk_points(const Plan& P) {
@@ -334,7 +347,7 @@ static int64_t bwd_chunk_points(const Plan& P, size_t ws_bytes) {
     int64_t need = (P.total_pts + 127) / 128 * 128;
     if (pc > need) pc = need;
     if (pc > (1 << 22)) pc = 1 << 22;
-    return pc;
+    return balanced_chunk_points(P.total_pts, pc);
 }
 
 enum { kBwdFull = 0, kBwdForwardOnly = 1, kBwdReuse = 2 };
