@@ -442,15 +442,28 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
                 ProfScope ps(kSlotPrep, st);
                 launch_prep_points(P.geom, d->npts, P.total_pts, p0, cb, q, status, st);
             }
+            // training forward: y / jets come out of the last hidden layer's epilogue when the shape allows it
+            TcFinal fin;
+            fin.w_last = (const float*)(ws + P.off_wh[L]);
+            fin.b_last = B[L];
+            fin.n_out = P.O;
+            fin.ldw = P.kp[L];
+            fin.y = y;
+            fin.jets = jets;
+            fin.p0 = p0;
+            fin.total_pts = P.total_pts;
+            const bool fuse = mode == kBwdForwardOnly && tc_bwd_can_fuse_final(tc, P.spec, dim, P.O);
             rc = tc_bwd_forward_chunk(tc, P.spec, dim, d->act_kind, d->act_param, cb, Vb, P.ncat, P.cat_off, Wx, act_last,
-                                      np_last, st);
+                                      np_last, fuse ? &fin : nullptr, st);
             if (rc) return fail(rc, "%s", tc_last_error());
-        }
-        if (mode == kBwdForwardOnly) {
-            ProfScope ps(kSlotFinal, st);
-            launch_final_blend(P.spec, dim, cb.rows, cb.pc, P.total_pts, p0, P.kp[L], P.O, act_last,
-                               (const float*)(ws + P.off_wh[L]), B[L], cb, y, jets, st);
-            break;
+            if (mode == kBwdForwardOnly) {
+                if (!fuse) {
+                    ProfScope ps(kSlotFinal, st);
+                    launch_final_blend(P.spec, dim, cb.rows, cb.pc, P.total_pts, p0, P.kp[L], P.O, act_last,
+                                       (const float*)(ws + P.off_wh[L]), B[L], cb, y, jets, st);
+                }
+                break;
+            }
         }
         {
             BlendBwdArgs a;

@@ -155,9 +155,15 @@ static void base_args(tc::LayerArgs& a, const TcBwdContext& tc, int dim, int act
     a.wait_ns = tc_env().wait_ns;
 }
 
+bool tc_bwd_can_fuse_final(const TcBwdContext& tc, const JetSpec& spec, int dim, int n_out) {
+    const TcBwdLayer& L = tc.layer[tc.n_layers - 2];
+    const bool pair = L.n_feat >= 2 * tc::kTileF && tc.use_pair_wide;
+    return tc_env().fuse_final && dim == 3 && spec_is_rb2(spec) && n_out <= 4 && !pair && L.n_feat <= tc::kTileF;
+}
+
 int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                          const float* Vb, int ncat, const int* cat_off, const float* const* Wx, float* act_last,
-                         int np_last, cudaStream_t st) {
+                         int np_last, const TcFinal* fused_final, cudaStream_t st) {
     if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_bwd_prepare");
     {
         ProfScope ps(kSlotLayer0, st);
@@ -181,6 +187,21 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
         a.out_f32 = act_last;
         a.z_out = L.z;
         a.ldz = L.ldz;
+        if (L.last && fused_final) {
+            a.fuse_final = 1;
+            a.n_out = fused_final->n_out;
+            a.ldw_last = fused_final->ldw;
+            a.w_last = fused_final->w_last;
+            a.b_last = fused_final->b_last;
+            a.pc = cb.pc;
+            a.p0 = fused_final->p0;
+            a.total_pts = fused_final->total_pts;
+            a.wfac = cb.wfac;
+            a.dfac = cb.dfac;
+            a.dxr = cb.dxr;
+            a.y = fused_final->y;
+            a.jets = fused_final->jets;
+        }
         int rc = L.last ? tc_encode_out_maps(a, spec.kc, act_last, nullptr, true)
                         : tc_encode_out_maps(a, spec.kc, a.out_hi, tc.passes == 3 ? (void*)a.out_lo : nullptr, false);
         if (rc) return rc;

@@ -48,7 +48,9 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
 // act_last = fp32 activations of the last hidden layer [kc][rows][np_last]
 int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
                          const float* Vb, int ncat, const int* cat_off, const float* const* Wx, float* act_last,
-                         int np_last, cudaStream_t st);
+                         int np_last, const struct TcFinal* fused_final, cudaStream_t st);
+// the training forward may fuse the final layer + blend into the last hidden layer's epilogue (it still writes act_last)
+bool tc_bwd_can_fuse_final(const TcBwdContext& tc, const JetSpec& spec, int dim, int n_out);
 
 // reverse sweep of one chunk; zbar of the last hidden layer must already be in layer[n-2].zb (blend_backward).
 // gW[l] : gradient of layer l's weight [widths[l]][in_features[l]] (scaled by S), g_vb [nvert][ncat]

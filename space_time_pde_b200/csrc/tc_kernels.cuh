@@ -156,6 +156,9 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -341,7 +344,10 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                                                   int n_cols, uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
     // scratch slot of one item: [0,128) x rows, [128,160) vertex indices, fused final only: [160,224) the point's blend
     // factors, [224,352) corner weights [8][w, dw/dq0, dw/dq1, dw/dq2]
-    constexpr uint32_t kSlot = OUTK == 3 ? 384 : 192;
+    constexpr bool kFuse = OUTK >= 3;                 // 3: fused final layer only, 4: fused final layer AND the fp32 plane
+    constexpr bool kF32 = OUTK == 2 || OUTK == 4;     // the staged output is the fp32 plane of the last hidden layer
+    constexpr bool kStage = OUTK != 3;
+    constexpr uint32_t kSlot = kFuse ? 384 : 192;
     constexpr int SRB = stage_rows(KC);
     constexpr int SR = (OUTK == 1 && SRB < 8) ? 2 * SRB : SRB;     // one plane only: twice the rows fit the buffer
     constexpr int NBUF = kEpiBuffers;
@@ -354,7 +360,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
     // ---- per-feature constants, reloaded when the feature tile changes ----
     float w5[4] = {0.f, 0.f, 0.f, 0.f};                              // fused final layer: this feature's column of W_last
     int cur_f0 = -1, g = 0;
-    bool g_ok = false, live = false;
+    bool g_ok = false, live = false, fuse_live = false;
     constexpr bool kRb2 = SPEC == kSpecRb2 && KC == 6;               // first-order components 1..3 <-> directions 0..2
     float sm = 0.f, wx[kMaxDim], wxc[kRb2 ? 1 : KC];                // wxc: constant tangent seed of first-order components
     auto load_feature_constants = [&](int f0) {
@@ -363,7 +369,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         g = fw + lane;
         g_ok = g < args.n_feat;
         live = fw < (OUTK == 3 ? args.n_feat : args.n_store) && has_blocks;
-        if constexpr (OUTK == 3) {
+        fuse_live = fw < args.n_feat;
+        if constexpr (kFuse) {
 #pragma unroll
             for (int o = 0; o < 4; ++o) w5[o] = (g_ok && o < args.n_out) ? __ldg(args.w_last + o * args.ldw_last + g) : 0.f;
         }
@@ -402,7 +409,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         const int rr = min(m.r0 + m.rb * 8 + (lane & 7), args.rows - 1);
         xv = __ldg(args.xrel + (int64_t)(lane >> 3) * args.rows + rr);
         vv = __ldg(args.vtx + rr);
-        if constexpr (OUTK == 3) {        // blend factors of the item's point: lanes 0..5 wfac, 6..11 dfac, 12..14 dxr
+        if constexpr (kFuse) {            // blend factors of the item's point: lanes 0..5 wfac, 6..11 dfac, 12..14 dxr
             const int ip = min((m.r0 + m.rb * 8) >> 3, args.pc - 1);
             const float* src = lane < 6 ? args.wfac + (int64_t)lane * args.pc
                              : lane < 12 ? args.dfac + (int64_t)(lane - 6) * args.pc
@@ -414,7 +421,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         const uint32_t a = row_addr + slot * kSlot;
         sts_f32(a + (lane & 7) * 16 + (lane >> 3) * 4, xv);
         if (lane < 8) sts_f32(a + 128 + lane * 4, __int_as_float(vv));
-        if constexpr (OUTK == 3) { if (lane < 16) sts_f32(a + 160 + lane * 4, pf); }
+        if constexpr (kFuse) { if (lane < 16) sts_f32(a + 160 + lane * 4, pf); }
     };
     // Vb gather of an item (its rows are in scratch slot `slot`) for THIS thread's feature of that item's tile
     auto gather_vb = [&](const Item& m, int slot, float* zraw) {
@@ -496,7 +503,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         //   acc[7], acc[8] = sum dw/dq_1 a_2, sum dw/dq_2 a_3           acc[9], acc[10] = sum w a_4, sum w a_5
         // and the (lane-uniform) sums of the corner weights sw[0] = sum w, sw[1..3] = sum dw/dq_k for the bias terms
         float acc[11], sw[4];
-        if constexpr (OUTK == 3) {
+        if constexpr (kFuse) {
 #pragma unroll
             for (int e = 0; e < 11; ++e) acc[e] = 0.f;
 #pragma unroll
@@ -519,7 +526,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         static_for<NPASS>([&](auto PS) {
             constexpr int ps = decltype(PS)::value;
             constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SRB * 128) : 0;
-            const uint32_t sl = stg_addr + kBufOff + lane * (OUTK == 2 ? 4 : 2);
+            const uint32_t sl = stg_addr + kBufOff + lane * (kF32 ? 4 : 2);
             // TL rows at a time leave TMEM (a whole 8-row block in registers does not fit the 96-register budget next to
             // the prefetched skip terms: spilling those made the spill store wait for the very load it was hiding)
             constexpr int TL = SR < 4 ? SR : 4;
@@ -579,7 +586,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                             o[c] = oc;
                         }
                     }
-                    if constexpr (OUTK == 3) {
+                    if constexpr (kFuse) {
                         const uint4 cw = lds_v4(row_addr + slot * kSlot + 224 + i * 16);
                         const float w = __uint_as_float(cw.x), d0 = __uint_as_float(cw.y), d1 = __uint_as_float(cw.z),
                                     d2 = __uint_as_float(cw.w);
@@ -589,7 +596,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                         acc[4] = fmaf(w, o[1], acc[4]); acc[5] = fmaf(w, o[2], acc[5]); acc[6] = fmaf(w, o[3], acc[6]);
                         acc[7] = fmaf(d1, o[2], acc[7]); acc[8] = fmaf(d2, o[3], acc[8]);
                         acc[9] = fmaf(w, o[4], acc[9]); acc[10] = fmaf(w, o[5], acc[10]);
-                    } else {
+                    }
+                    if constexpr (kStage) {
                     if constexpr (ir == 0) {
                         // the TMA engine must have read the buffer's previous contents (a tile ago when the block is one pass)
                         if (lane == 0) { if constexpr (NBUF > 1) bulk_wait_read1(); else bulk_wait_read0(); }
@@ -598,7 +606,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                     static_for<KC>([&](auto C) {
                         constexpr int c = decltype(C)::value;
                         const float xs = o[c];
-                        if constexpr (OUTK == 2) {
+                        if constexpr (kF32) {
                             sts_f32_o<(c * SR + ir) * 128>(sl, xs);
                         } else {
                             amax = fmaxf(amax, fabsf(xs));
@@ -611,7 +619,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                     }
                 });
             });
-            if constexpr (OUTK != 3) {
+            if constexpr (kStage) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -623,7 +631,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
             }
         });
         });
-        if constexpr (OUTK == 3) {
+        if constexpr (kFuse) {
+            if (fuse_live) {
             // ---- product rule of the blend (reference local_implicit_grid.py:57-61 + the jets), per feature ----
             const uint32_t pa = row_addr + slot * kSlot + 160;
             const float dx0 = __uint_as_float(lds_b32(pa + 48)), dx1 = __uint_as_float(lds_b32(pa + 52)),
@@ -672,6 +681,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                 if (c == 0) args.y[gp * args.n_out + o] = total;
                 else args.jets[((long long)(c - 1) * args.total_pts + gp) * args.n_out + o] = total;
             }
+            }
         }
         }
         // rows of the item after next -> the slot `cur` just vacated (every lane has read its x values above)
@@ -692,8 +702,8 @@ __device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArg
                                              int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
                                              uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
     if constexpr (CAN_FUSE) {
-        if (args.last && args.fuse_final) {
-            fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 3>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+        if (args.last && args.fuse_final) {     // training forward (MODE 1): the reverse sweep still needs the fp32 plane
+            fwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, MODE == kModeFwdSave ? 4 : 3>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
             return;
         }
     }
@@ -1216,7 +1226,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                 r0 = (t / n_ftiles) * NR;
                 return t < n_tiles;
             };
-            constexpr bool kCanFuse = MODE == kModeFwd && KC == 6 && SPEC == kSpecRb2;
+            constexpr bool kCanFuse = MODE < kModeBwd && KC == 6 && SPEC == kSpecRb2;
             fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, kCanFuse>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
                                                               smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratchFused,
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);

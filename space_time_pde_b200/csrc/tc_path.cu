@@ -59,17 +59,23 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
 // evaluated (the kernel is latency-bound on the Vb gather otherwise).
 // THREE (lo plane written) is a template parameter: the single-pass mode used to compute the lo halves and drop them
 // (30 of its 207 instructions per warp-row; the kernel is issue-bound in that mode, ncu r02).
-template <int KC, bool THREE>
-__global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, int dim, int act, float beta, int rows, int N,
-                                                                int ld, const int* __restrict__ vtx,
-                                                                const float* __restrict__ xrel, const float* __restrict__ Wx,
-                                                                const float* __restrict__ Vb, int ncat,
+// TMA_OUT: the 24 (48) halves a thread produces per row go to a per-warp smem staging buffer [plane][component][128
+// features] with 8-byte st.shared and leave through one cp.async.bulk.tensor store per plane and row (box 128 features x
+// 1 row x K) instead of 6 (12) st.global with 64-bit address arithmetic each.
+template <int KC, bool THREE, bool TMA_OUT>
+__global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
+                                                                const __grid_constant__ CUtensorMap map_lo, JetSpec spec, int dim,
+                                                                int act, float beta, int rows, int N, int ld,
+                                                                const int* __restrict__ vtx, const float* __restrict__ xrel,
+                                                                const float* __restrict__ Wx, const float* __restrict__ Vb, int ncat,
                                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                                 int* __restrict__ status) {
     constexpr int F = 4;
     const int fg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int n0 = (blockIdx.x * 32 + fg) * F;
-    if (n0 >= ld) return;
+    __shared__ __align__(128) uint8_t staging[TMA_OUT ? 8 : 1][TMA_OUT ? (THREE ? 2 : 1) * KC * 256 : 16];
+    if (!TMA_OUT && n0 >= ld) return;
+    const uint32_t stg = tc::smem_u32(&staging[TMA_OUT ? rl : 0][0]);
     float wx[F][kMaxDim];
 #pragma unroll
     for (int e = 0; e < F; ++e)
@@ -156,9 +162,27 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
                     pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
                 }
             }
-            const int64_t off = ((int64_t)c * rows + r) * ld + n0;
-            *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(ph[0], ph[1]);
-            if constexpr (THREE) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pl[0], pl[1]);
+            if constexpr (TMA_OUT) {
+                if (c == 0) {                                  // the previous row's stores have read the buffer
+                    if (fg == 0) tc::bulk_wait_read0();
+                    __syncwarp();
+                }
+                tc::sts_v2(stg + c * 256 + fg * 8, ph[0], ph[1]);
+                if constexpr (THREE) tc::sts_v2(stg + (KC + c) * 256 + fg * 8, pl[0], pl[1]);
+            } else {
+                const int64_t off = ((int64_t)c * rows + r) * ld + n0;
+                *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(ph[0], ph[1]);
+                if constexpr (THREE) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pl[0], pl[1]);
+            }
+        }
+        if constexpr (TMA_OUT) {
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (fg == 0) {
+                tc::tma_store_3d(&map_hi, stg, blockIdx.x * 128, r, 0);
+                if constexpr (THREE) tc::tma_store_3d(&map_lo, stg + KC * 256, blockIdx.x * 128, r, 0);
+                tc::bulk_commit();
+            }
         }
 #pragma unroll
         for (int k = 0; k < kMaxDim; ++k) xr[k] = xr_n[k];
@@ -166,6 +190,7 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(JetSpec spec, in
         for (int e = 0; e < F; ++e) vb[e] = vb_n[e];
     }
     });
+    if (TMA_OUT && fg == 0) tc::bulk_wait0();
     if (!(smax * cmax < 65000.f)) atomicOr(status, kStatusRange);
 }
 
@@ -249,6 +274,8 @@ const TcEnv& tc_env() {
         e.wait_ns = w ? (uint32_t)atoll(w) : 0x989680u;
         const char* f = getenv("STPDE_FUSE_FINAL");
         e.fuse_final = f ? atoi(f) : 1;
+        const char* l0 = getenv("STPDE_L0_TMA");
+        e.l0_tma = l0 ? atoi(l0) : 1;
         return e;
     }();
     return env;
@@ -359,29 +386,38 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
     return STPDE_OK;
 }
 
+// layer-0 launch: TMA-store variant unless STPDE_L0_TMA=0
 template <int KC>
-static void launch_layer0_tc(const TcContext& tc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb,
-                             int N, const float* Wx, const float* Vb, int ncat, cudaStream_t st) {
-    dim3 grid((tc.ld0 + 127) / 128, (cb.rows + 63) / 64);
-    if (tc.passes == 3)
-        layer0_jets_tc_kernel<KC, true><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb,
-                                                              ncat, tc.act[0][0], tc.act[0][1], tc.status);
-    else
-        layer0_jets_tc_kernel<KC, false><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, tc.ld0, cb.vtx, cb.xrel, Wx, Vb,
-                                                               ncat, tc.act[0][0], tc.act[0][1], tc.status);
+static void launch_layer0_any(const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
+                              const float* Wx, const float* Vb, int ncat, bool three, __half* out_hi, __half* out_lo,
+                              int* status, cudaStream_t st) {
+    dim3 grid((ld + 127) / 128, (cb.rows + 63) / 64);
+    CUtensorMap m_hi, m_lo;
+    bool tma = tc_env().l0_tma && encode_fn();
+    if (tma) {
+        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)cb.rows, (cuuint64_t)KC};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(__half), (cuuint64_t)ld * cb.rows * sizeof(__half)};
+        cuuint32_t box[3] = {(cuuint32_t)(ld < 128 ? ld : 128), 1, (cuuint32_t)KC};
+        cuuint32_t es[3] = {1, 1, 1};
+        void* planes[2] = {out_hi, three ? (void*)out_lo : (void*)out_hi};
+        CUtensorMap* maps[2] = {&m_hi, &m_lo};
+        for (int i = 0; i < 2 && tma; ++i)
+            tma = encode_fn()(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, planes[i], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        if (ld < 128) tma = false;                        // (the staging layout assumes 128-feature boxes)
+    }
+    if (!tma) { memset(&m_hi, 0, sizeof(m_hi)); memset(&m_lo, 0, sizeof(m_lo)); }
+#define STPDE_L0_LAUNCH(THREE_, TMA_) layer0_jets_tc_kernel<KC, THREE_, TMA_><<<grid, 256, 0, st>>>(m_hi, m_lo, spec, dim, act, beta, cb.rows, N, ld, \
+                                                                                      cb.vtx, cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)
+    if (three) { if (tma) STPDE_L0_LAUNCH(true, true); else STPDE_L0_LAUNCH(true, false); }
+    else       { if (tma) STPDE_L0_LAUNCH(false, true); else STPDE_L0_LAUNCH(false, false); }
+#undef STPDE_L0_LAUNCH
 }
 
 void tc_launch_layer0_planes(int kc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
                              const float* Wx, const float* Vb, int ncat, int three, __half* out_hi, __half* out_lo,
                              int* status, cudaStream_t st) {
-    dim3 grid((ld + 127) / 128, (cb.rows + 63) / 64);
-    if (three) {
-        STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC, true><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
-                                                                                        cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)));
-    } else {
-        STPDE_TC_DISPATCH_KC(kc, (layer0_jets_tc_kernel<KC, false><<<grid, 256, 0, st>>>(spec, dim, act, beta, cb.rows, N, ld, cb.vtx,
-                                                                                         cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)));
-    }
+    STPDE_TC_DISPATCH_KC(kc, (launch_layer0_any<KC>(spec, dim, act, beta, cb, N, ld, Wx, Vb, ncat, three != 0, out_hi, out_lo, status, st)));
 }
 
 bool tc_can_fuse_final(const TcContext& tc, const JetSpec& spec, int dim, int n_out) {
@@ -396,8 +432,8 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
     if (cb.rows != tc.rows) return tc_fail(STPDE_EINVAL, "chunk geometry changed after tc_prepare");
     {
         ProfScope ps(kSlotLayer0, st);
-        STPDE_TC_DISPATCH_KC(spec.kc, launch_layer0_tc<KC>(tc, spec, dim, act, beta, cb, tc.n0,
-                                                           (const float*)(ws + off_wx[0]), Vb, ncat, st));
+        tc_launch_layer0_planes(spec.kc, spec, dim, act, beta, cb, tc.n0, tc.ld0, (const float*)(ws + off_wx[0]), Vb, ncat,
+                                tc.passes == 3, tc.act[0][0], tc.act[0][1], tc.status, st);
     }
     for (int l = 1; l <= tc.n_layers - 2; ++l) {
         const TcLayerPlan& L = tc.layer[l];

@@ -14,6 +14,7 @@ struct TcEnv {
     int use_pair;
     uint32_t wait_ns;
     int fuse_final;      // STPDE_FUSE_FINAL=0: keep the separate final_blend kernel
+    int l0_tma;          // STPDE_L0_TMA=0: layer 0 writes its planes with st.global instead of TMA stores
 };
 
 // Final linear layer + multilinear blend fused into the epilogue of the last hidden layer (inference, d = 3, the

@@ -56,6 +56,8 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libstpde.so does not export {name}"
     assert set(_lib.EXPORTS) == declared
+    # every symbol of the shared object resolves at load time (nvcc -shared links with undefined symbols allowed)
+    ctypes.CDLL(_lib.LIB_PATH, mode=os.RTLD_NOW)
     assert lib.stpde_version() == 200
     assert lib.stpde_desc_size() == ctypes.sizeof(_lib.StpdeDesc)
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/s15; mkdir -p $O
+O=gpurun_out/s19; mkdir -p $O
 export STPDE_PARITY_REPORT=$PWD/$O/parity_report.jsonl
 timeout 1500 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"
 grep -E "^FAILED|passed|failed" $O/pytest.log | tail -10
@@ -14,3 +14,4 @@ python tools/sweep.py fp16 2>&1 | tail -6 | tee $O/sweep_fp16.log
 timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "bench ref rc=$?"; tail -c 300 $O/bench_ref.json
 du -sh $O
+for p in 16384 8192; do python tools/train_chunk_probe.py $p 40960 2>&1 | tail -2; done | tee $O/chunk_probe.log
