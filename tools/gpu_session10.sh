@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/s19; mkdir -p $O
+O=gpurun_out/s22; mkdir -p $O
 export STPDE_PARITY_REPORT=$PWD/$O/parity_report.jsonl
 timeout 1500 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"
 grep -E "^FAILED|passed|failed" $O/pytest.log | tail -10
