@@ -608,6 +608,36 @@ def reference_size_train_step(device, with_eager):
     out = {"config": f"{B} crops x {P} points, ImNet nf={nf} {ACT}, latent 4x16x16x32, RB2 + continuity, L1 losses"}
     out["fused_ms"] = time_it(fused_step, 20)
     out["points_per_s"] = B * P / (out["fused_ms"] * 1e-3)
+    from space_time_pde_b200 import jets as _jets
+    # (i) without the two host round trips per step for the calls' status words (deferred checks, STPDE_ASYNC=1)
+    os.environ["STPDE_ASYNC"] = "1"
+    try:
+        out["fused_async_ms"] = time_it(fused_step, 20)
+        _jets.check_pending(wait=True)
+    finally:
+        os.environ.pop("STPDE_ASYNC", None)
+    # (ii) the whole step (forward, residuals, losses, reverse sweep) recorded into ONE CUDA graph and replayed: the
+    # library never allocates or synchronises, so torch.cuda.graph can capture it; status words are read afterwards
+    try:
+        eager_loss = float(fused_step().detach())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fused_step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            graph_loss = fused_step()
+        out["cuda_graph_ms"] = time_it(graph.replay, 20)
+        _jets.check_captured(clear=True)
+        out["cuda_graph_loss_abs_diff"] = abs(float(graph_loss.detach()) - eager_loss)
+        out["points_per_s_cuda_graph"] = B * P / (out["cuda_graph_ms"] * 1e-3)
+        del graph
+    except Exception as exc:
+        out["cuda_graph_error"] = str(exc)[:200]
+        _jets._captured.clear()
+    _jets.release_workspaces()
     os.environ["STPDE_BACKWARD"] = "torch"
     os.environ["STPDE_RESIDUALS"] = "torch"
     try:

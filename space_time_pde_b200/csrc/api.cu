@@ -360,13 +360,17 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
                         float* const* gW, float* const* gB, float* ggrid, float* gbeta, float* y, float* jets, char* ws,
                         size_t ws_bytes, int* status, cudaStream_t st) {
     const int dim = d->dim, kc = P.spec.kc, L = P.n_layers - 1;
+    BufferList grads;               // decoder gradients: zeroed here, scaled by 1/S at the end, one launch each
+    grads.count = 0;
     if (mode != kBwdForwardOnly) {
         for (int l = 0; l < P.n_layers; ++l) {
-            CUDA_TRY(cudaMemsetAsync(gW[l], 0, (size_t)P.widths[l] * P.in_features[l] * sizeof(float), st));
-            CUDA_TRY(cudaMemsetAsync(gB[l], 0, (size_t)P.widths[l] * sizeof(float), st));
+            grads.add(gW[l], (int64_t)P.widths[l] * P.in_features[l]);
+            grads.add(gB[l], P.widths[l]);
         }
-        if (ggrid) CUDA_TRY(cudaMemsetAsync(ggrid, 0, (size_t)P.nvert_total * d->channels * sizeof(float), st));
-        if (gbeta) CUDA_TRY(cudaMemsetAsync(gbeta, 0, sizeof(float), st));
+        grads.add(gbeta, 1);
+        BufferList zero = grads;
+        zero.add(ggrid, (int64_t)P.nvert_total * d->channels);
+        launch_zero_buffers(zero, st);
     }
     if (P.total_pts == 0) return STPDE_OK;
     int64_t pc = bwd_chunk_points(P, ws_bytes);
@@ -489,7 +493,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
         if (rc) return fail(rc, "%s", tc_last_error());
     }
     if (mode != kBwdForwardOnly) {
-        ProfScope ps(kSlotBwdVertex, st, 3 + 2 * P.n_layers);
+        ProfScope ps(kSlotBwdVertex, st, 3);
         VertexBwdArgs v;
         memset(&v, 0, sizeof(v));
         v.n_layers = P.n_layers; v.ncat = P.ncat;
@@ -499,11 +503,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
         }
         v.grid = grid; v.g_vb = g_vb; v.scale = scale;
         launch_vertex_backward(P.geom, P.nvert_total, v, ggrid, st);
-        for (int l = 0; l < P.n_layers; ++l) {
-            launch_scale_buffer(gW[l], (int64_t)P.widths[l] * P.in_features[l], scale, st);
-            launch_scale_buffer(gB[l], P.widths[l], scale, st);
-        }
-        if (gbeta) launch_scale_buffer(gbeta, 1, scale, st);
+        launch_scale_buffers(grads, scale, st);
     }
     CUDA_TRY(cudaGetLastError());
     return STPDE_OK;

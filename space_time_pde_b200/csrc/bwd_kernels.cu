@@ -4,7 +4,7 @@
 //   blend_backward  : transpose of final_blend (product rule over the 2^d corners) + last linear layer
 //                     + reverse jet activation of the last hidden layer
 //   vertex_backward : adjoint of the per-vertex precompute Vb = b + W[:, latent cols] . latent
-//   scale_buffer    : final 1/S
+//   buffer_list     : zero fill / final 1/S of all gradient buffers in one launch
 // Mirrors the forward kernels of simt_kernels.cu; see DESIGN.md "Reverse mode".
 #include <cuda_fp16.h>
 
@@ -56,9 +56,15 @@ __global__ void grad_scale_kernel(JetSpec spec, GridGeom g, const unsigned* __re
     scale[1] = 1.f / S;
 }
 
-__global__ void scale_buffer_kernel(float* __restrict__ buf, int64_t n, const float* __restrict__ scale) {
-    const float s = scale[1];
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) buf[e] *= s;
+// one launch for every gradient buffer of a call (blockIdx.y = buffer): zero fill before the sweep, final 1/S after it
+// (the reference-size training step is launch-bound: 2 * n_layers + 2 separate memsets / scale kernels otherwise)
+template <bool SCALE>
+__global__ void buffer_list_kernel(const __grid_constant__ BufferList bl, const float* __restrict__ scale) {
+    float* __restrict__ buf = bl.ptr[blockIdx.y];
+    const int64_t n = bl.n[blockIdx.y];
+    const float s = SCALE ? scale[1] : 0.f;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        buf[e] = SCALE ? buf[e] * s : 0.f;
 }
 
 // W^T hi/lo [fp rows (f)][ldz (g)] = fp16 split of W[g][f] * 2^sw (the forward's per-layer scale, from its absmax)
@@ -259,10 +265,18 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
 // vertex_backward (weights): gb_l[n] = sum_v gVb[v][cat],  gW_l[n][kh + dim + ch] = sum_v gVb[v][cat] latent[v][ch]
 // block = 128 cats x one slice of kVbSlice vertices; channel tiles of 32 keep the accumulators in registers
 // ----------------------------------------------------------------------------------------------
-constexpr int kVbSlice = 32;      // vertices per block: enough blocks to fill the GPU for a 1024-vertex grid
+// vertices per block: a multiple of 16 sized so that ~4 blocks per SM exist - every block ends with one atomicAdd per
+// (cat, channel), so smaller slices only multiply the atomics on the same ncat x c addresses (10 M of them at 32
+// vertices per block for the reference-size step: 0.3 of its 3.3 ms)
+static int vb_slice(int nvert_total, int cat_blocks) {
+    const int want_slices = (148 * 4 + cat_blocks - 1) / cat_blocks;
+    int slice = (nvert_total + want_slices - 1) / want_slices;
+    slice = (slice + 15) / 16 * 16;
+    return slice < 32 ? 32 : slice;
+}
 
-__global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int nvert_total, VertexBwdArgs a) {
-    __shared__ float lat[16][33];
+__global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int nvert_total, VertexBwdArgs a, int kVbSlice) {
+    __shared__ __align__(16) float lat[16][32];
     const int cat = blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = cat < a.ncat;
     int l = 0;
@@ -301,7 +315,13 @@ __global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int 
                     const float gv = a.g_vb[(int64_t)(v0 + vi) * a.ncat + cat];
                     if (ct == 0) bsum += gv;
 #pragma unroll
-                    for (int ch = 0; ch < 32; ++ch) acc[ch] = fmaf(gv, lat[vi][ch], acc[ch]);
+                    for (int ch = 0; ch < 32; ch += 4) {               // (all threads read the same 16 bytes: broadcast)
+                        const float4 q = *reinterpret_cast<const float4*>(&lat[vi][ch]);
+                        acc[ch] = fmaf(gv, q.x, acc[ch]);
+                        acc[ch + 1] = fmaf(gv, q.y, acc[ch + 1]);
+                        acc[ch + 2] = fmaf(gv, q.z, acc[ch + 2]);
+                        acc[ch + 3] = fmaf(gv, q.w, acc[ch + 3]);
+                    }
                 }
             }
         }
@@ -316,43 +336,58 @@ __global__ void __launch_bounds__(128) vertex_backward_w_kernel(GridGeom g, int 
 }
 
 // vertex_backward (latent grid): ggrid[v][ch] += (1/S) sum_{cat in slice} gVb[v][cat] * W_l(cat)[n(cat)][kh + dim + ch]
-// block = 8 vertices x 32 channels x one slice of kGridCatSlice cats (blockIdx.z), cat tiles of 128 staged in shared
-// memory; ggrid is zeroed by the caller and the slices are added with atomics
+// A small GEMM [nvert x ncat] . [ncat x c]: block = 32 vertices x 32 channels x one slice of kGridCatSlice cats
+// (blockIdx.z); tiles of 64 cats of both operands are staged in shared memory, a thread owns 4 vertices of one channel
+// (one conflict-free W read and four broadcast 16-byte gVb reads per 4 cats and 16 FMAs).  ggrid is zeroed by the caller
+// and the slices are added with atomics.  (The first version re-read W from global memory for every 8 vertices: 0.25 ms
+// of the 3.2 ms reference-size training step.)
 constexpr int kGridCatSlice = 512;
+constexpr int kGridVerts = 32, kGridCats = 64;
 
 __global__ void __launch_bounds__(256) vertex_backward_grid_kernel(GridGeom g, int nvert_total, VertexBwdArgs a,
                                                                    float* __restrict__ ggrid) {
-    __shared__ float gv[8][128];
-    __shared__ const float* wrow[128];
-    const int ch = blockIdx.y * 32 + (threadIdx.x & 31);
-    const int vi = threadIdx.x >> 5;
-    const int v = blockIdx.x * 8 + vi;
+    __shared__ __align__(16) float gvt[kGridVerts][kGridCats];
+    __shared__ float wt[kGridCats][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.y * 32 + lane;
+    const int v0 = blockIdx.x * kGridVerts;
     const int c = g.channels;
     const int cat_begin = blockIdx.z * kGridCatSlice, cat_end = min(cat_begin + kGridCatSlice, a.ncat);
-    float acc = 0.f;
-    for (int cat0 = cat_begin; cat0 < cat_end; cat0 += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int cat0 = cat_begin; cat0 < cat_end; cat0 += kGridCats) {
         __syncthreads();
-        for (int e = threadIdx.x; e < 8 * 128; e += blockDim.x) {
-            const int vv = blockIdx.x * 8 + e / 128, cat = cat0 + e % 128;
-            gv[e / 128][e % 128] = (vv < nvert_total && cat < cat_end) ? a.g_vb[(int64_t)vv * a.ncat + cat] : 0.f;
+        for (int e = threadIdx.x; e < kGridVerts * kGridCats; e += blockDim.x) {
+            const int vi = e / kGridCats, t = e % kGridCats;
+            const int v = v0 + vi, cat = cat0 + t;
+            gvt[vi][t] = (v < nvert_total && cat < cat_end) ? a.g_vb[(int64_t)v * a.ncat + cat] : 0.f;
         }
-        if (threadIdx.x < 128) {
-            const int cat = cat0 + threadIdx.x;
-            const float* p = nullptr;
-            if (cat < cat_end) {
+        for (int t = warp; t < kGridCats; t += 8) {
+            const int cat = cat0 + t;
+            float w = 0.f;
+            if (cat < cat_end && ch < c) {
                 int l = 0;
                 while (l + 1 < a.n_layers - 1 && cat >= a.cat_off[l + 1]) ++l;
-                p = a.W[l] + (int64_t)(cat - a.cat_off[l]) * a.in_features[l] + a.kh[l] + g.dim;
+                w = __ldg(a.W[l] + (int64_t)(cat - a.cat_off[l]) * a.in_features[l] + a.kh[l] + g.dim + ch);
             }
-            wrow[threadIdx.x] = p;
+            wt[t][lane] = w;
         }
         __syncthreads();
-        if (ch < c) {
-            const int lim = min(128, cat_end - cat0);
-            for (int t = 0; t < lim; ++t) acc = fmaf(gv[vi][t], __ldg(wrow[t] + ch), acc);
+#pragma unroll 4
+        for (int t = 0; t < kGridCats; t += 4) {
+            const float w0 = wt[t][lane], w1 = wt[t + 1][lane], w2 = wt[t + 2][lane], w3 = wt[t + 3][lane];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 q = *reinterpret_cast<const float4*>(&gvt[warp * 4 + i][t]);
+                acc[i] = fmaf(q.x, w0, fmaf(q.y, w1, fmaf(q.z, w2, fmaf(q.w, w3, acc[i]))));
+            }
         }
     }
-    if (v < nvert_total && ch < c) atomicAdd(ggrid + (int64_t)v * c + ch, acc * a.scale[1]);
+    const float inv_s = a.scale[1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = v0 + warp * 4 + i;
+        if (v < nvert_total && ch < c) atomicAdd(ggrid + (int64_t)v * c + ch, acc[i] * inv_s);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -373,9 +408,18 @@ void launch_grad_scale(const JetSpec& spec, const GridGeom& g, const float* gy, 
     grad_scale_kernel<<<1, 32, 0, st>>>(spec, g, maxes, scale, target_exp);
 }
 
-void launch_scale_buffer(float* buf, int64_t n, const float* scale, cudaStream_t st) {
-    if (n <= 0) return;
-    scale_buffer_kernel<<<grid_for(n, 256), 256, 0, st>>>(buf, n, scale);
+static dim3 buffer_list_grid(const BufferList& bl) {
+    int64_t most = 1;
+    for (int i = 0; i < bl.count; ++i) most = bl.n[i] > most ? bl.n[i] : most;
+    return dim3((unsigned)grid_for(most, 256), (unsigned)bl.count);
+}
+
+void launch_zero_buffers(const BufferList& bl, cudaStream_t st) {
+    if (bl.count > 0) buffer_list_kernel<false><<<buffer_list_grid(bl), 256, 0, st>>>(bl, nullptr);
+}
+
+void launch_scale_buffers(const BufferList& bl, const float* scale, cudaStream_t st) {
+    if (bl.count > 0) buffer_list_kernel<true><<<buffer_list_grid(bl), 256, 0, st>>>(bl, scale);
 }
 
 void launch_split_weights_t(const float* W, int N, int in_features, int kh, int fp, int ldz, const unsigned* absmax,
@@ -420,10 +464,11 @@ int launch_blend_backward(const JetSpec& spec, const BlendBwdArgs& a, cudaStream
 }
 
 void launch_vertex_backward(const GridGeom& g, int nvert_total, const VertexBwdArgs& a, float* ggrid, cudaStream_t st) {
-    dim3 gw((a.ncat + 127) / 128, (nvert_total + kVbSlice - 1) / kVbSlice);
-    vertex_backward_w_kernel<<<gw, 128, 0, st>>>(g, nvert_total, a);
+    const int cat_blocks = (a.ncat + 127) / 128, slice = vb_slice(nvert_total, cat_blocks);
+    dim3 gw(cat_blocks, (nvert_total + slice - 1) / slice);
+    vertex_backward_w_kernel<<<gw, 128, 0, st>>>(g, nvert_total, a, slice);
     if (ggrid) {
-        dim3 gg((nvert_total + 7) / 8, (g.channels + 31) / 32, (a.ncat + kGridCatSlice - 1) / kGridCatSlice);
+        dim3 gg((nvert_total + kGridVerts - 1) / kGridVerts, (g.channels + 31) / 32, (a.ncat + kGridCatSlice - 1) / kGridCatSlice);
         vertex_backward_grid_kernel<<<gg, 256, 0, st>>>(g, nvert_total, a, ggrid);
     }
 }

@@ -45,7 +45,17 @@ struct VertexBwdArgs {
 
 void launch_grad_scale(const JetSpec& spec, const GridGeom& g, const float* gy, const float* gjets, int64_t plane_elems,
                        unsigned* maxes, float* scale, int target_exp, cudaStream_t st);
-void launch_scale_buffer(float* buf, int64_t n, const float* scale, cudaStream_t st);
+// up to 2 * kMaxLayers + 2 caller-owned gradient buffers handled by ONE launch
+struct BufferList {
+    float* ptr[2 * kMaxLayers + 2];
+    int64_t n[2 * kMaxLayers + 2];
+    int count;
+    void add(float* p, int64_t len) {
+        if (p && len > 0) { ptr[count] = p; n[count] = len; ++count; }
+    }
+};
+void launch_zero_buffers(const BufferList& bl, cudaStream_t st);
+void launch_scale_buffers(const BufferList& bl, const float* scale, cudaStream_t st);   // *= scale[1]
 void launch_split_weights_t(const float* W, int N, int in_features, int kh, int fp, int ldz, const unsigned* absmax,
                             __half* hi, __half* lo, cudaStream_t st);
 int launch_blend_backward(const JetSpec& spec, const BlendBwdArgs& a, cudaStream_t st);

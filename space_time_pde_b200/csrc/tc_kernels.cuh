@@ -57,8 +57,13 @@ __host__ __device__ constexpr int stage_rows(int kc) {
     return stage_rows_base(kc) / STPDE_EPI_SR_DIV > 0 ? stage_rows_base(kc) / STPDE_EPI_SR_DIV : 1;
 }
 // reverse mode: same staging granularity (a TMEM chunk never spans two staging passes: TL = min(rows per chunk, SR))
-__host__ __device__ constexpr int stage_rows_bwd(int kc) { return stage_rows(kc); }
+// K = 6 (the Rayleigh-Benard jet): 2 rows per pass, which leaves room for the z staging below
+__host__ __device__ constexpr int stage_rows_bwd(int kc) { return kc == 6 ? 2 : stage_rows(kc); }
 __host__ __device__ constexpr uint32_t epi_stage_bytes_bwd(int kc) { return (uint32_t)kc * stage_rows_bwd(kc) * 128u; }
+// reverse mode, K = 6: the saved z planes of a 2-row chunk (K x 2 rows x 32 features, fp32) are copied into shared memory
+// with cp.async while the PREVIOUS chunk is evaluated - loaded straight into registers, their L2 latency (~600 cycles,
+// four times per 8-row item, with only 4 warps per scheduler to hide it) was the top stall of the dgrad kernels (ncu r02)
+__host__ __device__ constexpr uint32_t z_stage_bytes(int kc) { return kc == 6 ? 6u * 2u * 128u : 0u; }
 __host__ __device__ constexpr uint32_t epi_stage_bytes(int kc) {
     return (uint32_t)kc * stage_rows(kc) * 128u * kEpiBuffers;
 }
@@ -225,6 +230,12 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr)
                  : "memory");
 }
+// 4-byte asynchronous copies global -> shared (LDGSTS): the reverse epilogue stages the z planes of its NEXT chunk
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -727,7 +738,7 @@ __device__ __forceinline__ void fwd_epilogue(const JetSpec& spec, const LayerArg
 // OUTK: 0 = zbar hi + lo planes, 1 = hi plane only (single-pass reverse sweep), ignored in MODE 3.
 template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, int OUTK, class TileFn, class HandBack>
 __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const LayerArgs& args, uint32_t stg_addr,
-                                                  uint32_t row_addr, int quarter, int sub, int lane, uint32_t tmem_q,
+                                                  uint32_t row_addr, uint32_t z_addr, int quarter, int sub, int lane, uint32_t tmem_q,
                                                   int n_cols, uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
     constexpr bool kBwd0 = MODE == kModeBwd0;
     constexpr uint32_t kSlot = 192;
@@ -737,6 +748,9 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
     constexpr int TL = kBwd0 ? HMAX : (SR < HMAX ? SR : HMAX);
     constexpr int NPASS = kBwd0 ? 1 : 8 / SR;
     constexpr int CHUNKS = kBwd0 ? 8 / TL : SR / TL;               // chunks per pass
+    constexpr bool ZST = !kBwd0 && z_stage_bytes(KC) > 0;          // z chunks staged through shared memory, one chunk ahead
+    constexpr uint32_t kZLane = KC * TL * 4;                       // bytes per lane: the lane's K x TL values, contiguous
+    static_assert(!ZST || (z_stage_bytes(KC) == 32 * kZLane && kZLane % 16 == 0), "z staging layout");
     const bool has_blocks = sub < NRB;
     const float scale = __ldg(args.wscale) * (float)(1 << kActScaleLog2);   // 2^-sw
     const int64_t zplane = (int64_t)args.rows * args.ldz;
@@ -847,6 +861,25 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
         }
     };
 
+    // MODE 2, K = 6: cp.async of the TL rows x K components of one chunk (first row `row0`, feature tile f0)
+    auto issue_z = [&](int f0, int row0) {
+        const int gm = f0 + quarter * 32 + lane;
+        if (gm < args.n_feat) {
+            const float* src = args.z_in + gm;
+            const uint32_t dst = z_addr + lane * kZLane;
+            static_for<TL>([&](auto JT) {
+                constexpr int j = decltype(JT)::value;
+                const float* srow = src + (int64_t)min(row0 + j, args.rows - 1) * args.ldz;
+                static_for<KC>([&](auto C) {
+                    constexpr int c = decltype(C)::value;
+                    cp_async_4(dst + (c * TL + j) * 4, srow + (int64_t)c * zplane);
+                });
+            });
+        }
+        cp_async_commit();
+    };
+    bool z_inflight = false;                                 // chunk 0 of `cur` was issued by the previous item
+
     Item cur{0, sub, 0, 0, false};
     cur.ok = tile(0, cur.f0, cur.r0);
     if (!cur.ok) return;
@@ -909,7 +942,10 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
         } else {
         const int rbase = cur.r0 + cur.rb * 8;
         const int fw = cur.f0 + quarter * 32;
-        const float* zbase = kBwd0 ? nullptr : args.z_in + (int64_t)rbase * args.ldz + (g_ok ? g : 0);
+        const float* zbase = (kBwd0 || ZST) ? nullptr : args.z_in + (int64_t)rbase * args.ldz + (g_ok ? g : 0);
+        if constexpr (ZST) {
+            if (!z_inflight) issue_z(cur.f0, rbase);
+        }
         dispatch_act(args.act, [&](auto act_c) {
         constexpr int kAct = decltype(act_c)::value;
         static_for<NPASS>([&](auto PS) {
@@ -922,7 +958,27 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
 #pragma unroll
                 for (int c = 0; c < KC; ++c) tmem_ld_n<TL>(taddr + cur.rb * (8 * KC) + c * 8 + i0, v[c]);
                 float zc[kBwd0 ? 1 : KC][TL];
-                if constexpr (!kBwd0) {
+                if constexpr (ZST) {
+                    cp_async_wait_all();                               // (each lane reads back only what it copied itself)
+                    float zf[KC * TL];
+                    static_for<KC * TL / 4>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        const uint4 t = lds_v4(z_addr + lane * kZLane + q * 16);
+                        zf[4 * q] = __uint_as_float(t.x); zf[4 * q + 1] = __uint_as_float(t.y);
+                        zf[4 * q + 2] = __uint_as_float(t.z); zf[4 * q + 3] = __uint_as_float(t.w);
+                    });
+#pragma unroll
+                    for (int c = 0; c < KC; ++c)
+#pragma unroll
+                        for (int j = 0; j < TL; ++j) zc[c][j] = g_ok ? zf[c * TL + j] : 0.f;
+                    // the next chunk's copies go into the same buffer: they land a memory latency after the reads above
+                    if constexpr (!(ps == NPASS - 1 && ch == CHUNKS - 1)) {
+                        issue_z(cur.f0, rbase + i0 + TL);
+                    } else {
+                        z_inflight = nxt.ok && nxt.f0 + quarter * 32 < args.n_store;
+                        if (z_inflight) issue_z(nxt.f0, nxt.r0 + nxt.rb * 8);
+                    }
+                } else if constexpr (!kBwd0) {
 #pragma unroll
                     for (int c = 0; c < KC; ++c)
 #pragma unroll
@@ -1068,19 +1124,19 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
 
 template <int KC, int MODE, int SPEC, int NRB, int EPI_PQ, class TileFn, class HandBack>
 __device__ __forceinline__ void bwd_epilogue(const JetSpec& spec, const LayerArgs& args, uint32_t stg, uint32_t rowbuf,
-                                             int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
+                                             uint32_t zbuf, int quarter, int sub, int lane, uint32_t tmem_q, int n_cols,
                                              uint32_t tfull_addr0, TileFn&& tile, HandBack&& hand_back) {
     if (MODE == kModeBwd0 || args.passes == 3)
-        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 0>(spec, args, stg, rowbuf, zbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
     else
-        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
+        bwd_epilogue_loop<KC, MODE, SPEC, NRB, EPI_PQ, 1>(spec, args, stg, rowbuf, zbuf, quarter, sub, lane, tmem_q, n_cols, tfull_addr0, tile, hand_back);
 }
 
-// bytes of output staging a kernel mode needs (all 16 epilogue warps); the reverse modes still store directly
+// bytes of output staging (+ row scratch, + z staging in reverse mode) a kernel mode needs (all 16 epilogue warps)
 template <int KC, int MODE, bool SINGLE = false>
 __host__ __device__ constexpr uint32_t epi_staging_total() {
     return MODE < kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes(KC) + (SINGLE ? kRowScratchFused : kRowScratch))
-           : MODE == kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes_bwd(KC) + kRowScratch)
+           : MODE == kModeBwd ? (uint32_t)kEpiWarps * (epi_stage_bytes_bwd(KC) + kRowScratch + z_stage_bytes(KC))
                               : (uint32_t)kEpiWarps * kRowScratch;           // MODE 3 writes no planes
 }
 
@@ -1218,6 +1274,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             constexpr uint32_t kStg = MODE == kModeBwd ? epi_stage_bytes_bwd(KC) : 0u;
             bwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * kStg,
                                                               smem_u32(staging) + kEpiWarps * kStg + (warp - 2) * kRowScratch,
+                                                              smem_u32(staging) + kEpiWarps * (kStg + kRowScratch) + (warp - 2) * z_stage_bytes(KC),
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         } else {
             auto tile = [&](int it, int& f0, int& r0) {
@@ -1449,6 +1506,7 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
             constexpr uint32_t kStg = MODE == kModeBwd ? epi_stage_bytes_bwd(KC) : 0u;
             bwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * kStg,
                                                               smem_u32(staging) + kEpiWarps * kStg + (warp - 2) * kRowScratch,
+                                                              smem_u32(staging) + kEpiWarps * (kStg + kRowScratch) + (warp - 2) * z_stage_bytes(KC),
                                                               quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         } else {
             fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, false>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),

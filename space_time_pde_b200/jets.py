@@ -67,6 +67,26 @@ def check_pending(wait: bool = False) -> None:
         _raise_for_status(err[0], f" [reported late: {err[1]} call under STPDE_ASYNC=1]")
 
 
+# CUDA-graph capture (torch.cuda.graph around a whole training / inference step): nothing may wait for the device while
+# the stream is capturing, so the calls' status words stay on the device; ``check_captured()`` reads them after a replay.
+# The backward cannot retry with more adjoint headroom inside a graph either - an overflow is reported, not repaired.
+_captured: list = []
+
+
+def _capturing(device: torch.device) -> bool:
+    return device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+
+
+def check_captured(clear: bool = False) -> None:
+    """Raise if a call recorded into a CUDA graph flagged an error during the latest replay (synchronises)."""
+    flags = [(int(t.item()), where) for t, where in _captured]
+    if clear:
+        _captured.clear()
+    for f, where in flags:
+        if f & 3:
+            _raise_for_status(f, f" [{where} call recorded in a CUDA graph]")
+
+
 def set_test_backend(fn) -> None:
     """Install a stand-in jet provider (tests of the host logic on machines without a GPU)."""
     global _test_backend
@@ -307,7 +327,9 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
                 jets[:nf] = sub_jets[:nf]
                 for i, pair in enumerate(sub.second):
                     jets[nf + spec.second.index(pair)] = sub_jets[nf + i]
-    if check:
+    if _capturing(device):
+        _captured.append((status, "forward"))
+    elif check:
         if os.environ.get("STPDE_ASYNC", "0") != "1":
             _raise_for_status(int(status.item()), "")
         else:
@@ -348,7 +370,8 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
     gwptr = (ctypes.c_void_p * len(gW))(*[w.data_ptr() for w in gW])
     gbptr = (ctypes.c_void_p * len(gB))(*[v.data_ptr() for v in gB])
     gstr, qstr = _i64(grid.stride()), _i64(q.stride())
-    sync = check and os.environ.get("STPDE_ASYNC", "0") != "1"
+    capturing = _capturing(device)
+    sync = check and not capturing and os.environ.get("STPDE_ASYNC", "0") != "1"
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         desc = make_desc(grid, q, lo, hi, widths, act, act_param, spec, precision)
@@ -372,9 +395,11 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
                                         ws.data_ptr(), ws.numel(), reuse, status.data_ptr(), stream)
             _lib.check(rc)
             if not sync:
-                # asynchronous mode: no retry with more headroom is possible without reading the flag back; the
-                # overflow is reported by a later call instead of being dropped
-                if check:
+                # asynchronous mode / graph capture: no retry with more headroom is possible without reading the flag
+                # back; the overflow is reported by a later call (check_captured() for a graph) instead of being dropped
+                if capturing:
+                    _captured.append((status, "backward"))
+                elif check:
                     check_pending()
                     _defer_status(status, "backward")
                 break

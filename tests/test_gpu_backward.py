@@ -184,6 +184,58 @@ def test_training_step_fused_vs_torch_route(dev, monkeypatch):
         assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4, i
 
 
+def test_training_step_replays_from_a_cuda_graph(dev):
+    """The library never allocates, synchronises or reads device values on the host, so a whole training step
+    (forward, residuals, loss, fused reverse sweep) can be recorded with torch.cuda.graph and replayed: the
+    reference-size step is launch-latency bound.  Status words are read after the replay (``check_captured``)."""
+    torch.manual_seed(0)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=16, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = (torch.randn(2, 4, 6, 5, 16) * 0.5).to(dev).requires_grad_(True)
+    q = torch.rand(2, 700, 3, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        grid.grad = None
+        y, res = layer(q)
+        loss = y.abs().mean() + 0.0125 * torch.stack(list(res.values())).abs().mean()
+        loss.backward()
+        return loss
+
+    eager_loss = float(step().detach())
+    eager = [grid.grad.clone()] + [p.grad.clone() for p in model.parameters()]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        loss = step()
+    captured = [grid.grad] + [p.grad for p in model.parameters()]
+    try:
+        with torch.no_grad():
+            q_new = torch.rand(2, 700, 3, device=dev)
+            q_old = q.clone()
+            q.copy_(q_new)                 # static input buffer: new points, same graph
+        graph.replay()
+        jets.check_captured()
+        assert abs(float(loss.detach()) - eager_loss) > 0          # the replay really used the new points
+        q.copy_(q_old)
+        graph.replay()
+        jets.check_captured()
+        assert abs(float(loss.detach()) - eager_loss) < 1e-6 * max(1.0, abs(eager_loss))
+        for i, (a, b) in enumerate(zip(captured, eager)):
+            assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-5, i      # (atomics: summation order differs)
+        assert len(jets._captured) == 2                   # forward + backward status words, still on the device
+    finally:
+        jets._captured.clear()
+        del graph
+        jets.release_workspaces()
+
+
 def test_backward_fallback_routes(dev):
     """Gradients w.r.t. the query points still work (torch route), and so does a decoder the kernel does not cover."""
     torch.manual_seed(1)
