@@ -82,8 +82,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"]
 
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(INCLUDE, "stpde.h")]
+    t_headers = max(os.path.getmtime(h) for h in headers)
+
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        # incremental: an object newer than its source and every header is kept
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(t_headers, os.path.getmtime(os.path.join(CSRC, src))):
+            return obj
         cmd = ["nvcc"] + flags + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)

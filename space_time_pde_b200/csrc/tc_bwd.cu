@@ -22,7 +22,8 @@ static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 size_t tc_bwd_fixed_bytes(int n_layers, const int* widths) {
     size_t off = 1024;   // wscale + absmax
     for (int l = 1; l <= n_layers - 2; ++l) {
-        const size_t w_plane = (size_t)round_up(widths[l], 256) * round_up(widths[l - 1], 64) * sizeof(__half);
+        const int pack = tc_layer_pack(widths[l], l == n_layers - 2);       // block-diagonal forward operand [128][pack * ld]
+        const size_t w_plane = (size_t)(pack > 1 ? 128 * pack : round_up(widths[l], 256)) * round_up(widths[l - 1], 64) * sizeof(__half);
         const size_t wt_plane = (size_t)round_up(widths[l - 1], 256) * round_up(widths[l], 64) * sizeof(__half);
         off += 2 * align_up(w_plane, 1024) + 2 * align_up(wt_plane, 1024);
     }
@@ -101,15 +102,16 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
         L.ldz = round_up(widths[l], 64);
         L.ld_in = round_up(widths[l - 1], 64);
         L.last = (l == n_layers - 2);
-        const int np256 = round_up(widths[l], 256), fp256 = round_up(widths[l - 1], 256);
-        const size_t w_plane = align_up((size_t)np256 * L.ld_in * sizeof(__half), 1024);
+        L.pack = tc_layer_pack(widths[l], L.last != 0);
+        const int np256 = L.pack > 1 ? 128 : round_up(widths[l], 256), fp256 = round_up(widths[l - 1], 256);
+        const size_t w_plane = align_up((size_t)np256 * L.ld_in * L.pack * sizeof(__half), 1024);
         const size_t wt_plane = align_up((size_t)fp256 * L.ldz * sizeof(__half), 1024);
         L.w_hi_ptr = (__half*)(fixed_ws + off); off += w_plane;
         L.w_lo_ptr = (__half*)(fixed_ws + off); off += w_plane;
         L.wt_hi_ptr = (__half*)(fixed_ws + off); off += wt_plane;
         L.wt_lo_ptr = (__half*)(fixed_ws + off); off += wt_plane;
         if (split_weights) {     // (a backward that reuses the training forward's workspace finds them in place)
-            tc_launch_split_weights(W[l], widths[l], in_features[l], L.kh, np256, L.ld_in, tc.absmax + l, tc.wscale + l,
+            tc_launch_split_weights(W[l], widths[l], in_features[l], L.kh, np256, L.ld_in, L.pack, tc.absmax + l, tc.wscale + l,
                                     L.w_hi_ptr, L.w_lo_ptr, st);
             launch_split_weights_t(W[l], widths[l], in_features[l], L.kh, fp256, L.ldz, tc.absmax + l, L.wt_hi_ptr, L.wt_lo_ptr, st);
         }
@@ -118,8 +120,8 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
             L.a_out[h] = L.last ? nullptr : a_planes[l][h];
             L.zb[h] = zb_planes[l & 1][h];
         }
-        rc |= tc_make_map_2d(&L.w_hi, L.w_hi_ptr, L.ld_in, np256, tc::kBlockK, tc::kTileF);
-        rc |= tc_make_map_2d(&L.w_lo, L.w_lo_ptr, L.ld_in, np256, tc::kBlockK, tc::kTileF);
+        rc |= tc_make_map_2d(&L.w_hi, L.w_hi_ptr, (uint64_t)L.ld_in * L.pack, np256, tc::kBlockK, tc::kTileF);
+        rc |= tc_make_map_2d(&L.w_lo, L.w_lo_ptr, (uint64_t)L.ld_in * L.pack, np256, tc::kBlockK, tc::kTileF);
         rc |= tc_make_map_3d(&L.fa_hi, L.a_in[0], L.ld_in, rows, kc, tc::kBlockK, 8, kc);
         rc |= tc_make_map_3d(&L.fa_lo, L.a_in[1], L.ld_in, rows, kc, tc::kBlockK, 8, kc);
         rc |= tc_make_map_2d(&L.wt_hi, L.wt_hi_ptr, L.ldz, fp256, tc::kBlockK, tc::kTileF);
@@ -179,6 +181,7 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
         a.ld_out = L.last ? np_last : L.ldz;
         a.n_store = a.ld_out;
         a.last = L.last;
+        a.pack = L.pack;
         a.cat_off = cat_off[l];
         a.wscale = tc.wscale + l;
         a.Wx = Wx[l];
@@ -244,6 +247,7 @@ static int launch_wgrad(const TcBwdContext& tc, const TcBwdLayer& L, float* gW, 
         if (eff > best + 1e-9) { best = eff; slices = sl; }
     }
     a.n_slices = (int)slices;
+    a.tile_fastest = tc_env().wgrad_tile_fastest;
     a.passes = tc.passes;
     a.out_scale = 1.f / (float)(1 << tc::kActScaleLog2);
     a.gW = gW;

@@ -14,7 +14,7 @@
 namespace stpde {
 
 struct TcBwdLayer {               // hidden layer l = 1 .. n_layers-2
-    int n_feat, kh, ldz, ld_in, last;
+    int n_feat, kh, ldz, ld_in, last, pack;   // pack: row groups per forward tile (tc_layer_pack)
     CUtensorMap w_hi, w_lo;       // forward: W_l planes [np256][ld_in], box 64 x 128
     CUtensorMap fa_hi, fa_lo;     // forward: a_{l-1} planes (ld_in, rows, kc), box 64 x 8 x kc
     CUtensorMap wt_hi, wt_lo;     // dgrad:   W_l^T planes [fp256][ldz], box 64 x 128
@@ -78,7 +78,7 @@ int tc_launch_single_bwd0(int kc, int num_sms, const CUtensorMap& w_hi, const CU
 int tc_make_map_2d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1);
 int tc_make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint32_t b2);
 bool tc_encode_available();
-void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int np, int kp, unsigned* absmax,
+void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int np, int kp, int pack, unsigned* absmax,
                              float* wscale, __half* hi, __half* lo, cudaStream_t st);
 void tc_launch_layer0_planes(int kc, const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
                              const float* Wx, const float* Vb, int ncat, int three, __half* out_hi, __half* out_lo,

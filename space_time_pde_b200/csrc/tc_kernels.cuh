@@ -281,6 +281,9 @@ struct LayerArgs {
     int n_store;       // features >= n_store are not written; [n_feat, n_store) are written as zeros
     int last;          // 1: write fp32 activations for final_blend, 0: write fp16 hi/lo planes
     int passes;        // 3 = hi/lo split, 1 = single fp16 pass
+    int pack;          // single-CTA kernel, narrow layers: G = 2 / 4 row groups share one 128-lane tile (block-diagonal
+                       // weight operand [128][G * kp_in]: group q's features sit in lanes q * 128/G ..., its K blocks in
+                       // columns q * kp_in ...), so every TMEM lane quarter has an epilogue to run; 0 / 1 = off
     int dim, act, ncat, cat_off;
     float beta;
     const float* wscale;   // device: 2^-(sw_l + sa) for this layer
@@ -1169,10 +1172,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kSingleMaxStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_ftiles = (args.n_store + kTileF - 1) / kTileF;
-    const int n_rtiles = (args.rows + NR - 1) / NR;
+    // Narrow layers (MODE 0 / 1): G row groups of NR rows per tile.  The contraction of group q runs over K blocks
+    // [q * kb_count, (q + 1) * kb_count) of the block-diagonal weight operand, whose only non-zero rows there are the
+    // lanes of group q - the other groups' accumulator lanes receive exact zeros from those blocks.
+    const int G = (MODE < kModeBwd && args.pack > 1) ? args.pack : 1;
+    const int n_ftiles = G > 1 ? 1 : (args.n_store + kTileF - 1) / kTileF;
+    const int n_rtiles = (args.rows + G * NR - 1) / (G * NR);
     const int n_tiles = n_ftiles * n_rtiles;
     const int kb_count = args.kp_in / kBlockK;
+    const int kb_total = G * kb_count;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
@@ -1197,23 +1205,24 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * NR;
-            for (int kb = 0; kb < kb_count; ++kb) {
+            const int f0 = (t % n_ftiles) * kTileF, r0 = (t / n_ftiles) * (G * NR);
+            for (int kq = 0, kb = 0, rq = r0; kq < kb_total; ++kq) {
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, args.status);
                 const uint32_t fb = smem_u32(&full_bar[stage]);
                 const uint32_t base = smem_u32(smem + stage * stage_bytes);
                 const uint32_t a_base = base + (three ? 2 * kWBytes : kWBytes);
                 if (elect_one()) {
                     mbar_expect_tx(fb, stage_bytes);
-                    tma_load_2d(base, &map_w_hi, kb * kBlockK, f0, fb);
-                    if (three) tma_load_2d(base + kWBytes, &map_w_lo, kb * kBlockK, f0, fb);
+                    tma_load_2d(base, &map_w_hi, kq * kBlockK, f0, fb);
+                    if (three) tma_load_2d(base + kWBytes, &map_w_lo, kq * kBlockK, f0, fb);
 #pragma unroll
                     for (int rb = 0; rb < NRB; ++rb) {
-                        tma_load_3d(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, r0 + rb * 8, 0, fb);
+                        tma_load_3d(a_base + rb * (8 * KC * 128), &map_a_hi, kb * kBlockK, rq + rb * 8, 0, fb);
                         if (three)
-                            tma_load_3d(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, r0 + rb * 8, 0, fb);
+                            tma_load_3d(a_base + kABytes + rb * (8 * KC * 128), &map_a_lo, kb * kBlockK, rq + rb * 8, 0, fb);
                     }
                 }
+                if (++kb == kb_count) { kb = 0; rq += NR; }      // next row group of the tile
                 __syncwarp();
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
@@ -1228,7 +1237,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * N;
-            for (int kb = 0; kb < kb_count; ++kb) {
+            for (int kb = 0; kb < kb_total; ++kb) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase, args.status);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + stage * stage_bytes);
@@ -1246,7 +1255,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));          // frees the smem stage when the MMAs retire
-                    if (kb == kb_count - 1) umma_commit(smem_u32(&tfull_bar[buf]));
+                    if (kb == kb_total - 1) umma_commit(smem_u32(&tfull_bar[buf]));
                 }
                 __syncwarp();
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -1257,6 +1266,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
         // Warp w may only touch TMEM lanes 32*(w%4)..+31; the warps of a quarter take the 8-row blocks in turn.
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
+        const int qpg = 4 / G;                               // lane quarters per row group
+        const int grp = quarter / qpg, fq = quarter - grp * qpg;   // row group / 32-feature block of this warp
         const uint32_t tmem_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
         // TMEM hand-back: the tcgen05.ld results are in registers (tcgen05.wait::ld), ordered before the arrive
         auto hand_back = [&](int buf) {
@@ -1280,13 +1291,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             auto tile = [&](int it, int& f0, int& r0) {
                 const int t = blockIdx.x + it * gridDim.x;
                 f0 = (t % n_ftiles) * kTileF;
-                r0 = (t / n_ftiles) * NR;
+                r0 = (t / n_ftiles) * (G * NR) + grp * NR;
                 return t < n_tiles;
             };
             constexpr bool kCanFuse = MODE < kModeBwd && KC == 6 && SPEC == kSpecRb2;
             fwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter, kCanFuse>(spec, args, smem_u32(staging) + (warp - 2) * epi_stage_bytes(KC),
                                                               smem_u32(staging) + kEpiWarps * epi_stage_bytes(KC) + (warp - 2) * kRowScratchFused,
-                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
+                                                              fq, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         }
     }
     tc_fence_before();

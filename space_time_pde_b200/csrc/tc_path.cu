@@ -33,8 +33,10 @@ __global__ void absmax_kernel(const float* __restrict__ W, int N, int in_feature
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
 }
 
-// Whi/Wlo [np128][kp] = fp16 split of W[:, :kh] * 2^sw with max|W| * 2^sw in [2^13, 2^14)
-__global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_features, int kh, int np128, int kp,
+// Whi/Wlo [np128][pack * kp] = fp16 split of W[:, :kh] * 2^sw with max|W| * 2^sw in [2^13, 2^14).
+// pack > 1 (narrow layers, tc_layer_pack): block diagonal - copy q of W sits in rows q * 128/pack ... and columns
+// q * kp ..., everything else is zero.
+__global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_features, int kh, int np128, int kp, int pack,
                                      const unsigned* __restrict__ absmax, float* __restrict__ wscale,
                                      __half* __restrict__ hi, __half* __restrict__ lo) {
     const float amax = __uint_as_float(*absmax);
@@ -43,10 +45,12 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
     const int sw = amax > 0.f ? 14 - e2 : 0;
     const float up = ldexpf(1.f, sw);
     if (blockIdx.x == 0 && threadIdx.x == 0) *wscale = ldexpf(1.f, -(sw + tc::kActScaleLog2));
-    const int64_t total = (int64_t)np128 * kp;
+    const int ldk = pack * kp, lanes = pack > 1 ? 128 / pack : np128;
+    const int64_t total = (int64_t)np128 * ldk;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int n = (int)(e / kp), k = (int)(e % kp);
-        float x = (n < N && k < kh) ? W[(int64_t)n * in_features + k] * up : 0.f;
+        const int row = (int)(e / ldk), col = (int)(e % ldk);
+        const int q = col / kp, k = col - q * kp, n = row - q * lanes;
+        float x = (n >= 0 && n < lanes && n < N && k < kh) ? W[(int64_t)n * in_features + k] * up : 0.f;
         __half h = __float2half_rn(x);
         hi[e] = h;
         lo[e] = __float2half_rn(x - __half2float(h));
@@ -65,7 +69,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int in_
 template <int KC, bool THREE, bool TMA_OUT>
 __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
                                                                 const __grid_constant__ CUtensorMap map_lo, JetSpec spec, int dim,
-                                                                int act, float beta, int rows, int N, int ld,
+                                                                int act, float beta, int rows, int rpw, int N, int ld,
                                                                 const int* __restrict__ vtx, const float* __restrict__ xrel,
                                                                 const float* __restrict__ Wx, const float* __restrict__ Vb, int ncat,
                                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
@@ -119,12 +123,12 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(const __grid_con
         }
     };
     float xr[kMaxDim], vb[F];
-    const int rbase = blockIdx.y * 64 + rl;
+    const int rbase = blockIdx.y * (8 * rpw) + rl;
     if (rbase < rows) load_row(rbase, xr, vb);
     dispatch_act(act, [&](auto act_c) {
     constexpr int kAct = decltype(act_c)::value;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < rpw; ++j) {
         const int r = rbase + 8 * j;
         if (r >= rows) break;
         float xr_n[kMaxDim], vb_n[F];
@@ -200,7 +204,8 @@ __global__ void __launch_bounds__(256, 3) layer0_jets_tc_kernel(const __grid_con
 size_t tc_fixed_bytes(int n_layers, const int* widths) {
     size_t off = 1024;  // wscale + absmax
     for (int l = 1; l <= n_layers - 2; ++l) {
-        size_t plane = (size_t)round_up(widths[l], 128) * round_up(widths[l - 1], 64) * sizeof(__half);
+        size_t plane = (size_t)round_up(widths[l], 128) * round_up(widths[l - 1], 64) * sizeof(__half) *
+                       tc_layer_pack(widths[l], l == n_layers - 2);
         off += 2 * align_up(plane, 1024);
     }
     return off;
@@ -276,9 +281,21 @@ const TcEnv& tc_env() {
         e.fuse_final = f ? atoi(f) : 1;
         const char* l0 = getenv("STPDE_L0_TMA");
         e.l0_tma = l0 ? atoi(l0) : 1;
+        const char* rpw = getenv("STPDE_L0_RPW");
+        e.l0_rows_per_warp = rpw && atoi(rpw) > 0 ? atoi(rpw) : 32;   // measured r02/s28: 8 -> 32 rows is 9-12 % faster
+        const char* wo = getenv("STPDE_WGRAD_ORDER");
+        e.wgrad_tile_fastest = wo ? atoi(wo) : 1;
+        const char* pk = getenv("STPDE_PACK");
+        e.pack_narrow = pk ? atoi(pk) : 1;
         return e;
     }();
     return env;
+}
+
+int tc_layer_pack(int n_feat, bool last) {
+    if (!tc_env().pack_narrow) return 1;
+    if (last) return round_up(n_feat, 16) <= 32 ? 4 : 1;
+    return n_feat <= 64 ? 2 : 1;
 }
 
 // TMA store maps of a layer's output planes [kc][rows][ld_out]: box = 32 features x stage_rows(kc) rows x kc components,
@@ -312,10 +329,10 @@ int tc_make_map_3d(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_
     return make_map_3d(m, base, d0, d1, d2, b0, b1, b2);
 }
 bool tc_encode_available() { return encode_fn() != nullptr; }
-void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int np, int kp, unsigned* absmax,
+void tc_launch_split_weights(const float* W, int N, int in_features, int kh, int np, int kp, int pack, unsigned* absmax,
                              float* wscale, __half* hi, __half* lo, cudaStream_t st) {
     absmax_kernel<<<148, 256, 0, st>>>(W, N, in_features, kh, absmax);
-    split_weights_kernel<<<148 * 4, 256, 0, st>>>(W, N, in_features, kh, np, kp, absmax, wscale, hi, lo);
+    split_weights_kernel<<<148 * 4, 256, 0, st>>>(W, N, in_features, kh, np, kp, pack, absmax, wscale, hi, lo);
 }
 
 int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
@@ -365,17 +382,18 @@ int tc_prepare(TcContext& tc, int precision, int n_layers, const int* widths, co
         L.last = (l == n_layers - 2);
         L.ld_out = L.last ? round_up(widths[l], 16) : round_up(widths[l], 64);
         L.n_store = L.ld_out;
-        const size_t plane = align_up((size_t)L.np128 * L.kp_in * sizeof(__half), 1024);
+        L.pack = tc_layer_pack(widths[l], L.last != 0);
+        const size_t plane = align_up((size_t)L.np128 * L.kp_in * L.pack * sizeof(__half), 1024);
         L.w_hi_ptr = (__half*)(fixed_ws + off); off += plane;
         L.w_lo_ptr = (__half*)(fixed_ws + off); off += plane;
         const int kh = widths[l - 1];
         if (split_weights) {     // (a call that reuses the previous call's setup finds the planes and scales in place)
             absmax_kernel<<<148, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, tc.absmax + l);
-            split_weights_kernel<<<148 * 4, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, L.np128, L.kp_in,
+            split_weights_kernel<<<148 * 4, 256, 0, st>>>(W[l], widths[l], in_features[l], kh, L.np128, L.kp_in, L.pack,
                                                           tc.absmax + l, tc.wscale + l, L.w_hi_ptr, L.w_lo_ptr);
         }
-        int rc = make_map_2d(&L.w_hi, L.w_hi_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
-        rc |= make_map_2d(&L.w_lo, L.w_lo_ptr, L.kp_in, L.np128, tc::kBlockK, tc::kTileF);
+        int rc = make_map_2d(&L.w_hi, L.w_hi_ptr, (uint64_t)L.kp_in * L.pack, L.np128, tc::kBlockK, tc::kTileF);
+        rc |= make_map_2d(&L.w_lo, L.w_lo_ptr, (uint64_t)L.kp_in * L.pack, L.np128, tc::kBlockK, tc::kTileF);
         __half* in_hi = tc.act[(l - 1) & 1][0];
         __half* in_lo = tc.act[(l - 1) & 1][1];
         rc |= make_map_3d(&L.a_hi, in_hi, L.kp_in, rows, kc, tc::kBlockK, 8, kc);
@@ -391,7 +409,11 @@ template <int KC>
 static void launch_layer0_any(const JetSpec& spec, int dim, int act, float beta, const ChunkBuffers& cb, int N, int ld,
                               const float* Wx, const float* Vb, int ncat, bool three, __half* out_hi, __half* out_lo,
                               int* status, cudaStream_t st) {
-    dim3 grid((ld + 127) / 128, (cb.rows + 63) / 64);
+    // rows per block: 8 warps x rpw rows (the per-thread feature constants are amortised over rpw rows); small chunks
+    // keep >= 16 blocks per SM
+    int rpw = tc_env().l0_rows_per_warp;
+    while (rpw > 8 && (int64_t)((ld + 127) / 128) * ((cb.rows + 8 * rpw - 1) / (8 * rpw)) < 16 * 148) rpw >>= 1;
+    dim3 grid((ld + 127) / 128, (cb.rows + 8 * rpw - 1) / (8 * rpw));
     CUtensorMap m_hi, m_lo;
     bool tma = tc_env().l0_tma && encode_fn();
     if (tma) {
@@ -407,7 +429,7 @@ static void launch_layer0_any(const JetSpec& spec, int dim, int act, float beta,
         if (ld < 128) tma = false;                        // (the staging layout assumes 128-feature boxes)
     }
     if (!tma) { memset(&m_hi, 0, sizeof(m_hi)); memset(&m_lo, 0, sizeof(m_lo)); }
-#define STPDE_L0_LAUNCH(THREE_, TMA_) layer0_jets_tc_kernel<KC, THREE_, TMA_><<<grid, 256, 0, st>>>(m_hi, m_lo, spec, dim, act, beta, cb.rows, N, ld, \
+#define STPDE_L0_LAUNCH(THREE_, TMA_) layer0_jets_tc_kernel<KC, THREE_, TMA_><<<grid, 256, 0, st>>>(m_hi, m_lo, spec, dim, act, beta, cb.rows, rpw, N, ld, \
                                                                                       cb.vtx, cb.xrel, Wx, Vb, ncat, out_hi, out_lo, status)
     if (three) { if (tma) STPDE_L0_LAUNCH(true, true); else STPDE_L0_LAUNCH(true, false); }
     else       { if (tma) STPDE_L0_LAUNCH(false, true); else STPDE_L0_LAUNCH(false, false); }
@@ -446,6 +468,7 @@ int tc_run_chunk(TcContext& tc, const JetSpec& spec, int dim, int act, float bet
         a.n_store = a.ld_out;
         a.last = L.last;
         a.passes = tc.passes;
+        a.pack = L.pack;
         a.dim = dim;
         a.act = act;
         a.ncat = ncat;

@@ -15,6 +15,9 @@ struct TcEnv {
     uint32_t wait_ns;
     int fuse_final;      // STPDE_FUSE_FINAL=0: keep the separate final_blend kernel
     int l0_tma;          // STPDE_L0_TMA=0: layer 0 writes its planes with st.global instead of TMA stores
+    int l0_rows_per_warp;     // STPDE_L0_RPW: rows one warp of the layer-0 kernel walks (block = 8 warps x this many rows)
+    int wgrad_tile_fastest;   // STPDE_WGRAD_ORDER=0: round-1 unit order of the weight-gradient kernel (slices of a tile adjacent)
+    int pack_narrow;          // STPDE_PACK=0: narrow layers (<= 64 features) keep one row group per 128-lane tile
 };
 
 // Final linear layer + multilinear blend fused into the epilogue of the last hidden layer (inference, d = 3, the
@@ -29,9 +32,13 @@ struct TcFinal {
 };
 bool tc_can_fuse_final(const struct TcContext& tc, const JetSpec& spec, int dim, int n_out);
 const TcEnv& tc_env();   // environment switches, read once per process
+// Row groups per tile of the single-CTA forward kernel (tc::LayerArgs::pack) for a hidden layer of n_feat features:
+// the last hidden layer stores round_up(n_feat, 16) features (4 groups when that is <= 32), the others 64-feature
+// multiples (2 groups when n_feat <= 64).  The weight operand of a packed layer is block diagonal [128][pack * kp].
+int tc_layer_pack(int n_feat, bool last);
 
 struct TcLayerPlan {
-    int n_feat, np128, kp_in, ld_out, n_store, last, cat_off;
+    int n_feat, np128, kp_in, ld_out, n_store, last, cat_off, pack;
     CUtensorMap w_hi, w_lo, a_hi, a_lo;
     __half *w_hi_ptr, *w_lo_ptr;
 };

@@ -29,6 +29,8 @@ struct WgradArgs {
     int nf_a, nf_b;        // true feature counts: M extent (widths[l-1]) and N extent (widths[l])
     int nt;                // N tile: 128 or 256
     int n_ft, n_gt, n_slices;
+    int tile_fastest;      // unit order: 1 = the tiles of one K slice are neighbours (concurrent CTA pairs share the slice's
+                           // operand rows through L2), 0 = the slices of one tile are neighbours (round 1; STPDE_WGRAD_ORDER=0)
     int passes;
     float out_scale;       // 2^-4: the a planes are stored scaled by 2^4
     float* gW;             // [nf_b][ldw]
@@ -49,6 +51,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
 // kind::f16 instruction descriptor with both operands MN-major (bits 15 / 16)
 __host__ __device__ constexpr uint32_t make_instr_desc_mn(int M, int N) {
     return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// work unit u -> (output tile, K slice)
+__device__ __forceinline__ void wgrad_unit(const WgradArgs& a, int u, int& tile, int& slice) {
+    const int n_tiles = a.n_ft * a.n_gt;
+    if (a.tile_fastest) { tile = u % n_tiles; slice = u / n_tiles; }
+    else                { slice = u % a.n_slices; tile = u / a.n_slices; }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -103,7 +112,8 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
         for (int u = pair_id; u < n_units; u += n_pairs) {
-            const int slice = u % args.n_slices, tile = u / args.n_slices;
+            int tile, slice;
+            wgrad_unit(args, u, tile, slice);
             const int f0 = (tile % args.n_ft) * kTileF2 + (int)rank * kTileF;
             const int g0 = (tile / args.n_ft) * args.nt + (int)rank * (args.nt / 2);
             const int64_t kb0 = total_kb * slice / args.n_slices, kb1 = total_kb * (slice + 1) / args.n_slices;
@@ -138,7 +148,8 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int u = pair_id; u < n_units; u += n_pairs, ++it) {
-                const int slice = u % args.n_slices;
+                int tile, slice;
+                wgrad_unit(args, u, tile, slice);
                 const int64_t kb0 = total_kb * slice / args.n_slices, kb1 = total_kb * (slice + 1) / args.n_slices;
                 const int buf = it & 1;
                 mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1, args.status);
@@ -178,8 +189,8 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int n_cg = args.nt / 8;
         int it = 0;
         for (int u = pair_id; u < n_units; u += n_pairs, ++it) {
-            const int tile = u / args.n_slices;
-            const int slice = u % args.n_slices;
+            int tile, slice;
+            wgrad_unit(args, u, tile, slice);
             const int64_t kb0 = total_kb * slice / args.n_slices, kb1 = total_kb * (slice + 1) / args.n_slices;
             const int buf = it & 1;
             const int f = (tile % args.n_ft) * kTileF2 + (int)rank * kTileF + quarter * 32 + lane;
