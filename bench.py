@@ -310,12 +310,15 @@ def leg_config2_train(ctx, args, model, grid, q, layer, peaks, lib):
             p_.grad = None
         reg_sum = torch.zeros((), device=device)
         pde_sum = torch.zeros((), device=device)
-        for s0 in range(0, NPTS, tchunk):
-            # residual programs + L1 reductions in ONE kernel (per-CTA partial sums; no [4,b,p] tensor, no torch.stack)
-            y, sums, _ = layer.loss_sums(q[:, s0:s0 + tchunk], None, "l1")
-            (sums[0] / (world * 4 * NPTS) + 0.0125 * sums[1] / (world * 4 * NPTS)).backward()
-            reg_sum += sums[0].detach()
-            pde_sum += sums[1].detach()
+        # deferred_checks: the calls' status words are read once at the end of the step (raised there), so the host
+        # launches chunk n+1 while the device still works on chunk n instead of idling through two round trips per chunk
+        with sp.deferred_checks():
+            for s0 in range(0, NPTS, tchunk):
+                # residual programs + L1 reductions in ONE kernel (per-CTA partial sums; no [4,b,p] tensor, no torch.stack)
+                y, sums, _ = layer.loss_sums(q[:, s0:s0 + tchunk], None, "l1")
+                (sums[0] / (world * 4 * NPTS) + 0.0125 * sums[1] / (world * 4 * NPTS)).backward()
+                reg_sum += sums[0].detach()
+                pde_sum += sums[1].detach()
         out["means"] = reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": 4 * NPTS, "pde": 4 * NPTS})
 
     try:
@@ -384,11 +387,12 @@ def leg_config3(ctx, args, peaks):
             p_.grad = None
         reg_sum = torch.zeros((), device=device)
         pde_sum = torch.zeros((), device=device)
-        for s0 in range(0, p_rank, chunk):
-            y, sums, _ = layer.loss_sums(q[:, s0:s0 + chunk], target[:, s0:s0 + chunk], "l1")
-            (sums[0] / n_glob + 0.0125 * sums[1] / n_glob).backward()
-            reg_sum += sums[0].detach()
-            pde_sum += sums[1].detach()
+        with sp.deferred_checks():                                # status words read once per step, not twice per chunk
+            for s0 in range(0, p_rank, chunk):
+                y, sums, _ = layer.loss_sums(q[:, s0:s0 + chunk], target[:, s0:s0 + chunk], "l1")
+                (sums[0] / n_glob + 0.0125 * sums[1] / n_glob).backward()
+                reg_sum += sums[0].detach()
+                pde_sum += sums[1].detach()
         out["means"] = reducer.reduce({"reg": reg_sum, "pde": pde_sum}, {"reg": n_glob / world, "pde": n_glob / world})
 
     try:

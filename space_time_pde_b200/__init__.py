@@ -11,9 +11,9 @@ from .pde import PDELayer, torch_diff
 from .physics import get_rb2_pde_layer
 from .regular_nd_grid_interpolation import (clip_tensor, regular_nd_grid_interpolation,
                                             regular_nd_grid_interpolation_coefficients)
-from .jets import fused_query, set_default_precision
+from .jets import deferred_checks, fused_query, set_default_precision
 from .equations import JetSpec
 
 __all__ = ["ImNet", "query_local_implicit_grid", "NONLINEARITIES", "Swish", "PDELayer", "torch_diff",
            "get_rb2_pde_layer", "clip_tensor", "regular_nd_grid_interpolation",
-           "regular_nd_grid_interpolation_coefficients", "fused_query", "set_default_precision", "JetSpec"]
+           "regular_nd_grid_interpolation_coefficients", "fused_query", "set_default_precision", "deferred_checks", "JetSpec"]

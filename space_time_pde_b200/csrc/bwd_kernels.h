@@ -56,7 +56,7 @@ struct BufferList {
 };
 void launch_zero_buffers(const BufferList& bl, cudaStream_t st);
 void launch_scale_buffers(const BufferList& bl, const float* scale, cudaStream_t st);   // *= scale[1]
-void launch_split_weights_t(const float* W, int N, int in_features, int kh, int fp, int ldz, const unsigned* absmax,
+void launch_split_weights_t(const float* W, int N, int in_features, int kh, int fp, int ldz, int pack, const unsigned* absmax,
                             __half* hi, __half* lo, cudaStream_t st);
 int launch_blend_backward(const JetSpec& spec, const BlendBwdArgs& a, cudaStream_t st);
 void launch_vertex_backward(const GridGeom& g, int nvert_total, const VertexBwdArgs& a, float* ggrid, cudaStream_t st);

@@ -103,9 +103,12 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
         L.ld_in = round_up(widths[l - 1], 64);
         L.last = (l == n_layers - 2);
         L.pack = tc_layer_pack(widths[l], L.last != 0);
-        const int np256 = L.pack > 1 ? 128 : round_up(widths[l], 256), fp256 = round_up(widths[l - 1], 256);
+        // dgrad of a layer whose INPUT has <= 64 features (MODE 2 only: layer 1's dgrad reverses the closed-form layer 0):
+        // 2 row groups per 128-lane tile, block-diagonal W^T [128][2 * ldz] (same bytes as the [256][ldz] plane)
+        L.pack_t = (l >= 2 && widths[l - 1] <= 64 && tc_env().pack_narrow) ? 2 : 1;
+        const int np256 = L.pack > 1 ? 128 : round_up(widths[l], 256), fp256 = L.pack_t > 1 ? 128 : round_up(widths[l - 1], 256);
         const size_t w_plane = align_up((size_t)np256 * L.ld_in * L.pack * sizeof(__half), 1024);
-        const size_t wt_plane = align_up((size_t)fp256 * L.ldz * sizeof(__half), 1024);
+        const size_t wt_plane = align_up((size_t)fp256 * L.ldz * L.pack_t * sizeof(__half), 1024);
         L.w_hi_ptr = (__half*)(fixed_ws + off); off += w_plane;
         L.w_lo_ptr = (__half*)(fixed_ws + off); off += w_plane;
         L.wt_hi_ptr = (__half*)(fixed_ws + off); off += wt_plane;
@@ -113,7 +116,7 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
         if (split_weights) {     // (a backward that reuses the training forward's workspace finds them in place)
             tc_launch_split_weights(W[l], widths[l], in_features[l], L.kh, np256, L.ld_in, L.pack, tc.absmax + l, tc.wscale + l,
                                     L.w_hi_ptr, L.w_lo_ptr, st);
-            launch_split_weights_t(W[l], widths[l], in_features[l], L.kh, fp256, L.ldz, tc.absmax + l, L.wt_hi_ptr, L.wt_lo_ptr, st);
+            launch_split_weights_t(W[l], widths[l], in_features[l], L.kh, fp256, L.ldz, L.pack_t, tc.absmax + l, L.wt_hi_ptr, L.wt_lo_ptr, st);
         }
         for (int h = 0; h < 2; ++h) {
             L.a_in[h] = a_planes[l - 1][h];
@@ -124,8 +127,8 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
         rc |= tc_make_map_2d(&L.w_lo, L.w_lo_ptr, (uint64_t)L.ld_in * L.pack, np256, tc::kBlockK, tc::kTileF);
         rc |= tc_make_map_3d(&L.fa_hi, L.a_in[0], L.ld_in, rows, kc, tc::kBlockK, 8, kc);
         rc |= tc_make_map_3d(&L.fa_lo, L.a_in[1], L.ld_in, rows, kc, tc::kBlockK, 8, kc);
-        rc |= tc_make_map_2d(&L.wt_hi, L.wt_hi_ptr, L.ldz, fp256, tc::kBlockK, tc::kTileF);
-        rc |= tc_make_map_2d(&L.wt_lo, L.wt_lo_ptr, L.ldz, fp256, tc::kBlockK, tc::kTileF);
+        rc |= tc_make_map_2d(&L.wt_hi, L.wt_hi_ptr, (uint64_t)L.ldz * L.pack_t, fp256, tc::kBlockK, tc::kTileF);
+        rc |= tc_make_map_2d(&L.wt_lo, L.wt_lo_ptr, (uint64_t)L.ldz * L.pack_t, fp256, tc::kBlockK, tc::kTileF);
         rc |= tc_make_map_3d(&L.zb_hi, L.zb[0], L.ldz, rows, kc, tc::kBlockK, 8, kc);
         rc |= tc_make_map_3d(&L.zb_lo, L.zb[1], L.ldz, rows, kc, tc::kBlockK, 8, kc);
         rc |= tc_make_map_3d(&L.ga_hi, L.a_in[0], L.ld_in, rows, kc, 64, tc::kWgKBlock, 1);
@@ -295,6 +298,7 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         const bool wide = L.kh >= 2 * tc::kTileF && tc.use_pair_wide;   // M extent of the dgrad = features of layer l-1
         int rc = STPDE_OK;
         if (l >= 2) {
+            a.pack = wide ? 0 : L.pack_t;
             a.z_in = tc.layer[l - 1].z;
             a.ldz = tc.layer[l - 1].ldz;
             a.out_hi = tc.layer[l - 1].zb[0];

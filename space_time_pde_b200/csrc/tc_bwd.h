@@ -14,7 +14,7 @@
 namespace stpde {
 
 struct TcBwdLayer {               // hidden layer l = 1 .. n_layers-2
-    int n_feat, kh, ldz, ld_in, last, pack;   // pack: row groups per forward tile (tc_layer_pack)
+    int n_feat, kh, ldz, ld_in, last, pack, pack_t;   // row groups per tile: forward (tc_layer_pack) / dgrad (block-diagonal W^T)
     CUtensorMap w_hi, w_lo;       // forward: W_l planes [np256][ld_in], box 64 x 128
     CUtensorMap fa_hi, fa_lo;     // forward: a_{l-1} planes (ld_in, rows, kc), box 64 x 8 x kc
     CUtensorMap wt_hi, wt_lo;     // dgrad:   W_l^T planes [fp256][ldz], box 64 x 128

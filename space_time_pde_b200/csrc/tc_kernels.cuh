@@ -1172,10 +1172,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kSingleMaxStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Narrow layers (MODE 0 / 1): G row groups of NR rows per tile.  The contraction of group q runs over K blocks
+    // Narrow layers (forward: <= 64 features; dgrad MODE 2: <= 64 features of the layer below): G row groups of NR rows per tile.  The contraction of group q runs over K blocks
     // [q * kb_count, (q + 1) * kb_count) of the block-diagonal weight operand, whose only non-zero rows there are the
     // lanes of group q - the other groups' accumulator lanes receive exact zeros from those blocks.
-    const int G = (MODE < kModeBwd && args.pack > 1) ? args.pack : 1;
+    const int G = args.pack > 1 ? args.pack : 1;
     const int n_ftiles = G > 1 ? 1 : (args.n_store + kTileF - 1) / kTileF;
     const int n_rtiles = (args.rows + G * NR - 1) / (G * NR);
     const int n_tiles = n_ftiles * n_rtiles;
@@ -1279,14 +1279,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
             auto tile = [&](int it, int& f0, int& r0) {
                 const int t = blockIdx.x + it * gridDim.x;
                 f0 = (t % n_ftiles) * kTileF;
-                r0 = (t / n_ftiles) * NR;
+                r0 = (t / n_ftiles) * (G * NR) + grp * NR;
                 return t < n_tiles;
             };
             constexpr uint32_t kStg = MODE == kModeBwd ? epi_stage_bytes_bwd(KC) : 0u;
             bwd_epilogue<KC, MODE, SPEC, NRB, kEpiPerQuarter>(spec, args, smem_u32(staging) + (warp - 2) * kStg,
                                                               smem_u32(staging) + kEpiWarps * kStg + (warp - 2) * kRowScratch,
                                                               smem_u32(staging) + kEpiWarps * (kStg + kRowScratch) + (warp - 2) * z_stage_bytes(KC),
-                                                              quarter, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
+                                                              fq, sub, lane, tmem_q, N, smem_u32(&tfull_bar[0]), tile, hand_back);
         } else {
             auto tile = [&](int it, int& f0, int& r0) {
                 const int t = blockIdx.x + it * gridDim.x;

@@ -133,7 +133,7 @@ static int launch_layer_mode(int num_sms, const CUtensorMap& w_hi, const CUtenso
             return tc_fail(STPDE_ECUDA, "cudaFuncSetAttribute(tc_layer_kernel, training mode) failed");
         configured.mark();
     }
-    const int rpt = NR * ((MODE < tc::kModeBwd && a.pack > 1) ? a.pack : 1);
+    const int rpt = NR * (a.pack > 1 ? a.pack : 1);
     const int n_tiles = rpt > NR ? (a.rows + rpt - 1) / rpt : ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     tc::tc_layer_kernel<KC, SPEC, MODE><<<grid, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);

@@ -6,6 +6,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import itertools
 import os
@@ -28,6 +29,28 @@ DEFAULT_PRECISION = os.environ.get("STPDE_PRECISION", "fp16x3")
 # the call instead, and every later call (or ``check_pending()``) raises for the calls that have finished since - errors
 # are delayed, never dropped.
 _pending: list = []
+
+
+def _async_mode() -> bool:
+    return os.environ.get("STPDE_ASYNC", "0") == "1" or getattr(_state, "deferred", 0) > 0
+
+
+@contextlib.contextmanager
+def deferred_checks():
+    """No call inside the block waits for its status word (as under ``STPDE_ASYNC=1``); leaving the block synchronises on
+    all of them and raises for the first error.  For loops over chunks of one step: the host keeps launching while the
+    device works instead of idling through two round trips per chunk.  (The backward cannot repeat itself with more
+    adjoint headroom in this mode: an fp16 overflow of an adjoint is reported, not repaired.)"""
+    _state.deferred = getattr(_state, "deferred", 0) + 1
+    try:
+        yield
+    except BaseException:
+        _state.deferred -= 1
+        raise
+    else:
+        _state.deferred -= 1
+        if _state.deferred == 0:
+            check_pending(wait=True)
 
 
 def _raise_for_status(flags: int, where: str) -> None:
@@ -330,7 +353,7 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
     if _capturing(device):
         _captured.append((status, "forward"))
     elif check:
-        if os.environ.get("STPDE_ASYNC", "0") != "1":
+        if not _async_mode():
             _raise_for_status(int(status.item()), "")
         else:
             check_pending()
@@ -371,7 +394,7 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
     gbptr = (ctypes.c_void_p * len(gB))(*[v.data_ptr() for v in gB])
     gstr, qstr = _i64(grid.stride()), _i64(q.stride())
     capturing = _capturing(device)
-    sync = check and not capturing and os.environ.get("STPDE_ASYNC", "0") != "1"
+    sync = check and not capturing and not _async_mode()
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         desc = make_desc(grid, q, lo, hi, widths, act, act_param, spec, precision)

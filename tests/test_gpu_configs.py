@@ -237,3 +237,22 @@ def test_async_mode_reports_errors_late_but_never_drops_them(dev, monkeypatch):
         jets.check_pending(wait=True)
     jets.check_pending(wait=True)                                                # reported once
     assert torch.isfinite(y).all() and y_bad.shape == y.shape
+
+
+def test_deferred_checks_block_raises_at_its_end_and_matches_the_checked_calls(dev):
+    """sp.deferred_checks(): a chunk loop inside the block never waits for a status word; the block's end raises for an
+    out-of-grid chunk; the numbers of the calls are the checked calls' numbers."""
+    torch.manual_seed(13)
+    model = sp.ImNet(dim=3, in_features=8, out_features=4, nf=8, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = torch.randn(1, 3, 4, 5, 8, device=dev) * 0.5
+    q = torch.rand(1, 600, 3, device=dev)
+    with torch.no_grad():
+        y_ref = sp.query_local_implicit_grid(model, grid, q, 0., 1.)
+        with sp.deferred_checks():
+            ys = [sp.query_local_implicit_grid(model, grid, q[:, s0:s0 + 200], 0., 1.) for s0 in range(0, 600, 200)]
+        assert torch.equal(torch.cat(ys, 1), y_ref)
+        with pytest.raises(IndexError):
+            with sp.deferred_checks():
+                sp.query_local_implicit_grid(model, grid, q + 2.0, 2., 3.)     # quirk Q1, reported when the block ends
+                sp.query_local_implicit_grid(model, grid, q, 0., 1.)
+    jets.check_pending(wait=True)                                              # nothing left over

@@ -397,3 +397,32 @@ def test_non_polynomial_equations_keep_the_torch_route():
     layer.add_equation("dif(u, t) + sin(u) * dif(u, x)", "burgers_like")
     spec, program = layer._binding()
     assert spec is not None and program is None and layer._adjoint is None
+
+
+def test_deferred_checks_scope_and_late_report():
+    """deferred_checks(): inside the block the calls' status words are not waited for (jets._async_mode()); leaving the
+    outermost block reads every pending word and raises for the first error; an exception inside the block is not masked."""
+    from space_time_pde_b200 import jets
+
+    class Ev:                                             # stand-in for a finished CUDA event
+        def synchronize(self):
+            pass
+
+        def query(self):
+            return True
+
+    assert not jets._async_mode()
+    with sp.deferred_checks():
+        assert jets._async_mode()
+        with sp.deferred_checks():
+            assert jets._async_mode()
+        assert jets._async_mode()                         # still inside the outer block: nothing was read yet
+    assert not jets._async_mode()
+    with pytest.raises(IndexError, match="reported late"):
+        with sp.deferred_checks():
+            jets._pending.append((Ev(), torch.tensor([1], dtype=torch.int32), "forward"))
+    assert not jets._pending and not jets._async_mode()
+    with pytest.raises(ZeroDivisionError):
+        with sp.deferred_checks():
+            1 / 0
+    assert not jets._async_mode()
