@@ -274,6 +274,50 @@ def oracle_parity(model, grid, q, y, res, n, rb2_kwargs=None, equations=None, ac
     return out
 
 
+def imnet_widths(nf):
+    """Hidden widths of ImNet (reference src/implicit_net.py:28-33): nf*16, nf*8, nf*4, nf*2, nf."""
+    return [nf * 16, nf * 8, nf * 4, nf * 2, nf]
+
+
+def plane_bytes_per_point(nf, d, kc, precision, training=False, fused_final=True):
+    """ALGORITHMIC HBM bytes per query point of the layer-by-layer design: every activation plane is
+    written once and read once by the next layer; a training step adds the fp32 pre-activations (written by the forward,
+    read by the dgrad epilogues), the zbar planes and the wgrad operand reads.  Planes are [kc][rows][width padded to 64]
+    fp16, hi + lo in the 3-pass mode.  At ImNet nf = 32 this, not the tensor pipe, bounds the step."""
+    P = 2 if precision == "fp16x3" else 1
+    w = imnet_widths(nf)
+    ld = [(x + 63) // 64 * 64 for x in w]
+    np_last = (w[-1] + 15) // 16 * 16
+    a = lambda l: ld[l] * kc * 2 * P                 # activation / zbar plane bytes per row of layer l
+    z = lambda l: ld[l] * kc * 4                     # fp32 pre-activations
+    n = len(w)
+    b = a(0)                                         # layer 0 writes its planes
+    for l in range(1, n):
+        b += a(l - 1)                                # operand read
+        if l < n - 1:
+            b += a(l)
+        elif training or not fused_final:
+            b += np_last * kc * 4                    # fp32 plane of the last hidden layer
+        if training:
+            b += z(l)
+    if training:
+        b += z(n - 1) + np_last * kc * 4 + a(n - 1)              # blend_backward
+        for l in range(n - 1, 0, -1):
+            b += a(l - 1) + a(l)                                 # wgrad operands
+            b += a(l)                                            # dgrad operand
+            if l >= 2:
+                b += z(l - 1) + a(l - 1)                         # saved pre-activations in, zbar planes out
+    return b * (1 << d)
+
+
+def hbm_roofline_of(rate_per_gpu, bytes_per_point, peaks):
+    gbs = rate_per_gpu * bytes_per_point / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+            "bytes_per_point": bytes_per_point,
+            "what": "algorithmic plane bytes per point (each plane written once, read once; training adds the saved "
+                    "pre-activations, the zbar planes and the wgrad operand reads) over the measured copy bandwidth"}
+
+
 def roofline_of(rate_per_gpu, fpt, peaks, passes, mult=1.0):
     tf = rate_per_gpu * fpt * mult / 1e12
     return {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
@@ -417,6 +461,7 @@ def leg_config3(ctx, args, peaks):
                 "value": rate, "unit": "points/s (training step)", "ms_per_step": ms, "scaling": "strong (fixed 8 M points)",
                 "points_per_rank": B * p_rank, "chunk_points": B * chunk,
                 "roofline": roofline_of(rate / world, fpt, peaks, 1, mult=3.0),
+                "roofline_hbm": hbm_roofline_of(rate / world, plane_bytes_per_point(nf, 3, KC, "fp16", training=True), peaks),
                 "parity": dict(par, mode="relaxed 16-bit mode: forward values + residuals vs fp64 oracle"),
                 "kernel_ms_per_step": {k: round(v[0], 2) for k, v in prof.items() if v[1] > 0},
                 "gpu_launches_per_step": int(sum(v[1] for v in prof.values())),
@@ -526,6 +571,7 @@ def leg_config5(ctx, args, peaks, precision, lib):
             "imnet_nf": nf, "jet_components": KC, "dtype": f"f32 I/O, {precision} contractions", "scaling": "strong",
             "flops_per_point": fpt, "sweep": rows, "value": rows[-1]["value"], "unit": UNIT,
             "roofline": roofline_of(rows[-1]["value"] / world, fpt, peaks, {"fp16x3": 3, "fp16": 1}.get(precision, 0)),
+            "roofline_hbm": hbm_roofline_of(rows[-1]["value"] / world, plane_bytes_per_point(nf, 3, KC, precision), peaks),
             "parity": par}
 
 
@@ -569,6 +615,9 @@ def leg_eval_grid(ctx, args, peaks, precision):
                         f"bounds [0, ({t_max}, 1, 4)] as tensors, stride-0 expanded batch, latent {list(latent.shape)} "
                         f"(permuted view), ImNet nf={nf}, values + RB2 residuals, ONE call",
             "value": n_query / (ms * 1e-3), "unit": UNIT, "ms": ms, "dtype": f"f32 I/O, {precision} contractions",
+            "roofline": roofline_of(n_query / (ms * 1e-3), flops_per_point(nf, 3, CHANNELS, 4, KC), peaks,
+                                    {"fp16x3": 3, "fp16": 1}.get(precision, 0)),
+            "roofline_hbm": hbm_roofline_of(n_query / (ms * 1e-3), plane_bytes_per_point(nf, 3, KC, precision), peaks),
             "pseudo_batch_loop": {"value": n_pb * pb / (ms_pb * 1e-3), "unit": UNIT, "batch": pb, "batches_timed": n_pb,
                                   "what": "the same decode called in the reference's 10 000-point pseudo-batches "
                                           "(evaluation.py:54-69) - per-call setup is paid every batch"}}
