@@ -256,3 +256,27 @@ def test_deferred_checks_block_raises_at_its_end_and_matches_the_checked_calls(d
                 sp.query_local_implicit_grid(model, grid, q + 2.0, 2., 3.)     # quirk Q1, reported when the block ends
                 sp.query_local_implicit_grid(model, grid, q, 0., 1.)
     jets.check_pending(wait=True)                                              # nothing left over
+
+
+def test_row_group_packing_is_bitwise_neutral(tmp_path):
+    """Narrow layers run 2 / 4 row groups per 128-lane tile against a block-diagonal weight operand (tc_layer_pack); the
+    other groups' K blocks add exact zeros, so forward values, jets and residuals are BITWISE those of one group per tile
+    (STPDE_PACK=0, a process-wide switch: two subprocesses); gradients agree to the atomics' summation-order noise."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for pk in ("0", "1"):
+        f = str(tmp_path / f"pack{pk}.npz")
+        env = dict(os.environ, STPDE_PACK=pk)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "pack_probe.py"), f], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        files.append(np.load(f))
+    a, b = files
+    assert set(a.files) == set(b.files) and len(a.files) >= 60
+    for k in a.files:
+        if k.startswith(("ggrid", "gw")):
+            assert rel_linf(b[k], a[k]) < 1e-5, k
+        else:
+            assert np.array_equal(a[k], b[k]), k
