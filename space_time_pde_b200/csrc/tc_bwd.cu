@@ -265,7 +265,11 @@ static int launch_wgrad(const TcBwdContext& tc, const TcBwdLayer& L, float* gW, 
     }
     const int n_units = a.n_ft * a.n_gt * a.n_slices;
     const int n_pairs = n_units < n_pairs_max ? n_units : n_pairs_max;
-    tc::tc_wgrad_pair_kernel<<<2 * n_pairs, tc::kThreads, smem, st>>>(L.ga_hi, L.ga_lo, L.gb_hi, L.gb_lo, a);
+    {
+        void* kargs[] = {(void*)&L.ga_hi, (void*)&L.ga_lo, (void*)&L.gb_hi, (void*)&L.gb_lo, (void*)&a};
+        if (tc_launch_ex((const void*)tc::tc_wgrad_pair_kernel, 2 * n_pairs, tc::kThreads, smem, st, kargs) != cudaSuccess)
+            return tc_fail(STPDE_ECUDA, "tc_wgrad_pair_kernel launch failed");
+    }
     return STPDE_OK;
 }
 

@@ -122,6 +122,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch (the host launches the tensor-core kernels with
+// cudaLaunchAttributeProgrammaticStreamSerialization, tc_launch_ex): griddep_wait() returns when the previous kernel in the
+// stream has completed and its writes are visible - everything a kernel does before it (barrier init, TMEM allocation,
+// descriptor prefetch, cluster sync) overlaps that kernel's tail; griddep_launch_dependents() lets the NEXT kernel's CTAs
+// take the SMs this grid's CTAs leave.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
@@ -1200,6 +1207,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();          // no global memory is read or written above this line
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -1428,6 +1437,8 @@ tc_layer_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();          // no global memory is read or written above this line
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop; one elected lane per CTA issues) =====================

@@ -1,6 +1,8 @@
 // Launch wrappers of the tensor-core layer kernels.  The kernel templates are instantiated for K = 1..10 jet
 // components in three separate translation units (tc_layers_a/b/c.cu) so that the build parallelises.
 #pragma once
+#include <cstring>
+
 #include "tc_kernels.cuh"
 #include "tc_path.h"
 
@@ -58,7 +60,30 @@ static inline bool spec_is_rb2(const JetSpec& s) {
 // Fills a.out_map for the output planes of a forward layer launch (tc_path.cu).
 int tc_encode_out_maps(tc::LayerArgs& a, int kc, void* plane0, void* plane1, bool f32, bool reverse = false);
 
+// Launch of a tensor-core kernel with programmatic stream serialization (STPDE_PDL=0: plain launch): the kernel's
+// prologue runs while the previous kernel in the stream drains; griddep_wait() in the kernel orders the data.
+static inline cudaError_t tc_launch_ex(const void* func, unsigned grid, unsigned block, size_t smem, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tc_env().pdl ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, func, args);
+}
+
 #ifdef STPDE_TC_LAUNCH_IMPL
+#define STPDE_TC_LAUNCH(KERNEL, GRID, SMEM, ST, M0, M1, M2, M3, SPEC_, ARGS_)                                           \
+    do {                                                                                                                 \
+        void* kargs_[] = {(void*)&(M0), (void*)&(M1), (void*)&(M2), (void*)&(M3), (void*)&(SPEC_), (void*)&(ARGS_)};     \
+        if (tc_launch_ex((const void*)(KERNEL), (unsigned)(GRID), tc::kThreads, (SMEM), (ST), kargs_) != cudaSuccess)    \
+            return tc_fail(STPDE_ECUDA, "tensor-core kernel launch failed");                                             \
+    } while (0)
 template <int KC, int SPEC = 0>
 static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec& spec, const tc::LayerArgs& a,
                         cudaStream_t st) {
@@ -75,7 +100,7 @@ static int launch_layer(const TcContext& tc, const TcLayerPlan& L, const JetSpec
     const int rpt = NR * (a.pack > 1 ? a.pack : 1);            // packed narrow layers: pack row groups per tile
     const int n_tiles = a.pack > 1 ? (a.rows + rpt - 1) / rpt : ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < tc.num_sms ? n_tiles : tc.num_sms;
-    tc::tc_layer_kernel<KC, SPEC><<<grid, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    STPDE_TC_LAUNCH((tc::tc_layer_kernel<KC, SPEC>), grid, smem, st, L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -93,7 +118,7 @@ static int launch_layer_pair(const TcContext& tc, const TcLayerPlan& L, const Je
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = tc.num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, tc::kModeFwd, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
+    STPDE_TC_LAUNCH((tc::tc_layer_pair_kernel<KC, tc::kModeFwd, SPEC>), 2 * n_pairs, smem, st, L.w_hi, L.w_lo, L.a_hi, L.a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -114,7 +139,7 @@ static int launch_layer_pair_mode(int num_sms, const CUtensorMap& w_hi, const CU
     const int n_tiles = ((a.n_store + 2 * tc::kTileF - 1) / (2 * tc::kTileF)) * ((a.rows + NR - 1) / NR);
     const int max_pairs = num_sms / 2;
     const int n_pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    tc::tc_layer_pair_kernel<KC, MODE, SPEC><<<2 * n_pairs, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    STPDE_TC_LAUNCH((tc::tc_layer_pair_kernel<KC, MODE, SPEC>), 2 * n_pairs, smem, st, w_hi, w_lo, a_hi, a_lo, spec, a);
     return STPDE_OK;
 }
 
@@ -136,7 +161,7 @@ static int launch_layer_mode(int num_sms, const CUtensorMap& w_hi, const CUtenso
     const int rpt = NR * (a.pack > 1 ? a.pack : 1);
     const int n_tiles = rpt > NR ? (a.rows + rpt - 1) / rpt : ((a.n_store + tc::kTileF - 1) / tc::kTileF) * ((a.rows + NR - 1) / NR);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    tc::tc_layer_kernel<KC, SPEC, MODE><<<grid, tc::kThreads, smem, st>>>(w_hi, w_lo, a_hi, a_lo, spec, a);
+    STPDE_TC_LAUNCH((tc::tc_layer_kernel<KC, SPEC, MODE>), grid, smem, st, w_hi, w_lo, a_hi, a_lo, spec, a);
     return STPDE_OK;
 }
 

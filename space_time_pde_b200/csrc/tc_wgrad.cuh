@@ -107,6 +107,8 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();          // no global memory is read or written above this line
 
     if (warp == 0) {
         // ===================== TMA producer =====================
