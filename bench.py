@@ -282,14 +282,14 @@ def imnet_widths(nf):
 def plane_bytes_per_point(nf, d, kc, precision, training=False, fused_final=True):
     """ALGORITHMIC HBM bytes per query point of the layer-by-layer design: every activation plane is
     written once and read once by the next layer; a training step adds the fp32 pre-activations (written by the forward,
-    read by the dgrad epilogues), the zbar planes and the wgrad operand reads.  Planes are [kc][rows][width padded to 64]
+    read by the dgrad epilogues; fp16 when forward and reverse sweep both run in the single-pass mode), the zbar planes and the wgrad operand reads.  Planes are [kc][rows][width padded to 64]
     fp16, hi + lo in the 3-pass mode.  At ImNet nf = 32 this, not the tensor pipe, bounds the step."""
     P = 2 if precision == "fp16x3" else 1
     w = imnet_widths(nf)
     ld = [(x + 63) // 64 * 64 for x in w]
     np_last = (w[-1] + 15) // 16 * 16
     a = lambda l: ld[l] * kc * 2 * P                 # activation / zbar plane bytes per row of layer l
-    z = lambda l: ld[l] * kc * 4                     # fp32 pre-activations
+    z = lambda l: ld[l] * kc * (2 if precision == "fp16" else 4)   # saved pre-activations: fp16 in the single-pass mode, else fp32
     n = len(w)
     b = a(0)                                         # layer 0 writes its planes
     for l in range(1, n):

@@ -112,7 +112,9 @@ typedef struct stpde_desc {
     int32_t precision;
     float xmin[STPDE_MAX_DIM];          /* float32 bounds exactly as the reference forms them */
     float xmax[STPDE_MAX_DIM];
-    int32_t reserved[8];                /* [0]: backward only, extra headroom bits of the adjoint scale (0 = default)
+    int32_t reserved[8];                /* [2]: stpde_jet_backward with reuse_forward = 1: set to 1 when the forward that left
+                                           the planes ran with precision STPDE_PREC_FP16 (its pre-activation planes are fp16)
+                                           [0]: backward only, extra headroom bits of the adjoint scale (0 = default)
                                          * [1]: stpde_jet_forward only, 1 = the call-invariant part of the workspace (packed /
                                          *      split weights, per-vertex latent + bias table) is still valid from the
                                          *      previous call on the SAME workspace with the same decoder weights, latent

@@ -435,8 +435,11 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
     prof_end(kSlotSetup, st, P.n_layers + 4);
 
     TcBwdContext tc;
+    // The saved pre-activations are fp16 planes when the forward that writes (wrote) them runs in the single-pass mode:
+    // this call's own precision, or - reverse sweep on a stash (kBwdReuse) - what the caller reports in reserved[2].
+    const bool z_half = tc_env().z_half && (mode == kBwdReuse ? d->reserved[2] == 1 : d->precision == STPDE_PREC_FP16);
     int rc = tc_bwd_prepare(tc, d->precision, P.n_layers, P.widths, P.in_features, W, ws + P.off_tc, tc_chunk,
-                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, prep, st);
+                            (size_t)(ws + ws_bytes - tc_chunk), kc, (int)rows, status, prep, z_half, st);
     if (rc) return fail(rc, "%s", tc_last_error());
 
     const TcBwdLayer& TL = tc.layer[P.n_layers - 2];
@@ -478,7 +481,7 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
             a.total_pts = P.total_pts; a.p0 = p0; a.cb = cb;
             a.gy = gy; a.gjets = gjets; a.scale = scale;
             a.Wlast = (const float*)(ws + P.off_wh[L]);
-            a.act_last = act_last; a.z_in = TL.z;
+            a.act_last = act_last; a.z_in = TL.z; a.z_half = tc.z_half;
             a.out_hi = TL.zb[0]; a.out_lo = TL.zb[1];
             a.g_vb = g_vb;
             a.g_wx = gW[L - 1] + P.kh[L - 1]; a.g_wx_ld = P.in_features[L - 1];

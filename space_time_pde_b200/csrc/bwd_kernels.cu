@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(JetSpec spec, Blend
                 float z[KC], ab[KC], av[KC];
 #pragma unroll
                 for (int c = 0; c < KC; ++c) {
-                    z[c] = a.z_in[(int64_t)c * zplane + (int64_t)r * a.ldz + f];
+                    const int64_t ze = (int64_t)c * zplane + (int64_t)r * a.ldz + f;
+                    z[c] = a.z_half ? __half2float(reinterpret_cast<const __half*>(a.z_in)[ze]) : a.z_in[ze];
                     av[c] = a.act_last[(int64_t)c * aplane + (int64_t)r * Kp + f];
                 }
 #pragma unroll

@@ -11,6 +11,7 @@ namespace stpde {
 
 struct BlendBwdArgs {
     int dim, rows, O, Kp, n_feat, ld_out, ldz, act, ncat, cat_off, three;
+    int z_half;             // 1: z_in holds fp16 (single-pass training), 0: fp32
     int acc_copies;         // set by the launcher: private per-warp accumulator copies in shared memory (8) or 1
     float beta;
     int64_t total_pts, p0;

@@ -53,7 +53,7 @@ size_t tc_bwd_per_point_bytes(int n_layers, const int* widths, int kc, int ncorn
 // ---------------------------------------------------------------------------------------------
 int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                    const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-                   int* status, bool split_weights, cudaStream_t st) {
+                   int* status, bool split_weights, bool z_half, cudaStream_t st) {
     if (!tc_encode_available()) return tc_fail(STPDE_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
     if (n_layers < 3) return tc_fail(STPDE_EUNSUPPORTED, "the tensor-core backward needs at least one hidden contraction");
     if (rows % tc::kWgKBlock) return tc_fail(STPDE_EINVAL, "chunk rows must be a multiple of 64");
@@ -72,6 +72,7 @@ int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* wid
     tc.ld0 = round_up(widths[0], 64);
     tc.n0 = widths[0];
     tc.use_pair_wide = tc_env().use_pair;
+    tc.z_half = z_half ? 1 : 0;
 
     // chunk planes
     char* p = chunk_ws;
@@ -193,6 +194,7 @@ int tc_bwd_forward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int act
         a.out_f32 = act_last;
         a.z_out = L.z;
         a.ldz = L.ldz;
+        a.z_half = tc.z_half;
         if (L.last && fused_final) {
             a.fuse_final = 1;
             a.n_out = fused_final->n_out;
@@ -303,6 +305,7 @@ int tc_bwd_backward_chunk(TcBwdContext& tc, const JetSpec& spec, int dim, int ac
         int rc = STPDE_OK;
         if (l >= 2) {
             a.pack = wide ? 0 : L.pack_t;
+            a.z_half = tc.z_half;
             a.z_in = tc.layer[l - 1].z;
             a.ldz = tc.layer[l - 1].ldz;
             a.out_hi = tc.layer[l - 1].zb[0];

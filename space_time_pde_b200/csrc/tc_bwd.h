@@ -13,6 +13,8 @@
 
 namespace stpde {
 
+// TcBwdContext::z_half: the saved pre-activations z_l are fp16 planes (the forward that wrote them ran in the single-pass
+// mode); set by tc_bwd_prepare from its z_half argument, read by the forward-save, dgrad and blend_backward launches.
 struct TcBwdLayer {               // hidden layer l = 1 .. n_layers-2
     int n_feat, kh, ldz, ld_in, last, pack, pack_t;   // row groups per tile: forward (tc_layer_pack) / dgrad (block-diagonal W^T)
     CUtensorMap w_hi, w_lo;       // forward: W_l planes [np256][ld_in], box 64 x 128
@@ -30,7 +32,7 @@ struct TcBwdLayer {               // hidden layer l = 1 .. n_layers-2
 
 struct TcBwdContext {
     int n_layers, kc, rows, passes, num_sms, use_pair_wide;
-    int ld0, n0;
+    int ld0, n0, z_half;
     TcBwdLayer layer[kMaxLayers];
     float* wscale;
     unsigned* absmax;
@@ -42,7 +44,7 @@ size_t tc_bwd_per_point_bytes(int n_layers, const int* widths, int kc, int ncorn
 
 int tc_bwd_prepare(TcBwdContext& tc, int precision, int n_layers, const int* widths, const int* in_features,
                    const float* const* W, char* fixed_ws, char* chunk_ws, size_t chunk_bytes, int kc, int rows,
-                   int* status, bool split_weights, cudaStream_t st);
+                   int* status, bool split_weights, bool z_half, cudaStream_t st);
 
 // forward recompute of one chunk: layer 0 + hidden layers, all operand planes and pre-activations kept;
 // act_last = fp32 activations of the last hidden layer [kc][rows][np_last]

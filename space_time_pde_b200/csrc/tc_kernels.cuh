@@ -306,6 +306,8 @@ struct LayerArgs {
     float* z_out;          // MODE 1: pre-activations of this layer, fp32 [KC][rows][ldz]
     const float* z_in;     // MODE 2: pre-activations of the layer whose adjoints this launch produces
     int ldz;               // row stride of z_out / z_in
+    int z_half;            // 1: z_out / z_in planes hold fp16 (training entirely in the single-pass mode: the saved
+                           // pre-activations are 30 % of that step's HBM bytes as fp32), 0: fp32
     float* g_vb;           // MODE 2/3: adjoint of Vb, [nvert][ncat] (atomics)
     float* g_wx;           // MODE 2/3: adjoint of the coordinate columns, &gW[0][kh], row stride g_wx_ld (atomics)
     int g_wx_ld;
@@ -577,10 +579,22 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
                         const int r = rbase + i;
                         if (g_ok && r < args.rows) {           // pre-activations for the reverse sweep
                             const int64_t zplane = (int64_t)args.rows * args.ldz;
-                            float* pz = args.z_out + (int64_t)r * args.ldz + g;
-                            *pz = z0;
+                            if (args.z_half) {                 // (warp-uniform)
+                                __half* pz = reinterpret_cast<__half*>(args.z_out) + (int64_t)r * args.ldz + g;
+                                *pz = __float2half_rn(z0);
+                                amax = fmaxf(amax, fabsf(z0));
 #pragma unroll
-                            for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
+                                for (int c = 1; c < KC; ++c) {
+                                    pz += zplane;
+                                    *pz = __float2half_rn(zt[c]);
+                                    amax = fmaxf(amax, fabsf(zt[c]));      // range flag: the caller retries in fp16x3
+                                }
+                            } else {
+                                float* pz = args.z_out + (int64_t)r * args.ldz + g;
+                                *pz = z0;
+#pragma unroll
+                                for (int c = 1; c < KC; ++c) { pz += zplane; *pz = zt[c]; }
+                            }
                         }
                     }
                     s0 *= sm; s1 *= sm; s2 *= sm;
@@ -866,15 +880,32 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
         if (gm0 < args.n_feat) {
             for (int idx = lane; idx < KC * 8; idx += 32) {
                 const int rn = min(m.r0 + m.rb * 8 + (idx & 7), args.rows - 1);
-                prefetch_l2(args.z_in + (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + gm0);
+                const int64_t e = (int64_t)(idx >> 3) * zplane + (int64_t)rn * args.ldz + gm0;
+                prefetch_l2(args.z_half ? (const void*)(reinterpret_cast<const __half*>(args.z_in) + e) : (const void*)(args.z_in + e));
             }
         }
     };
 
     // MODE 2, K = 6: cp.async of the TL rows x K components of one chunk (first row `row0`, feature tile f0)
+    // fp16 planes (args.z_half): a 4-byte copy holds the values of a lane PAIR (features 2k, 2k + 1); the pair shares one
+    // kZLane-byte slot and each of its lanes issues every other (component, row) entry
     auto issue_z = [&](int f0, int row0) {
         const int gm = f0 + quarter * 32 + lane;
-        if (gm < args.n_feat) {
+        if (args.z_half) {
+            const int gp = gm & ~1;
+            if (gp < args.n_feat) {
+                const __half* src = reinterpret_cast<const __half*>(args.z_in) + gp;
+                const uint32_t dst = z_addr + (lane >> 1) * kZLane;
+                static_for<TL>([&](auto JT) {
+                    constexpr int j = decltype(JT)::value;
+                    const __half* srow = src + (int64_t)min(row0 + j, args.rows - 1) * args.ldz;
+                    static_for<KC>([&](auto C) {
+                        constexpr int c = decltype(C)::value;
+                        if (((c * TL + j) & 1) == (lane & 1)) cp_async_4(dst + (c * TL + j) * 4, srow + (int64_t)c * zplane);
+                    });
+                });
+            }
+        } else if (gm < args.n_feat) {
             const float* src = args.z_in + gm;
             const uint32_t dst = z_addr + lane * kZLane;
             static_for<TL>([&](auto JT) {
@@ -952,7 +983,9 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
         } else {
         const int rbase = cur.r0 + cur.rb * 8;
         const int fw = cur.f0 + quarter * 32;
-        const float* zbase = (kBwd0 || ZST) ? nullptr : args.z_in + (int64_t)rbase * args.ldz + (g_ok ? g : 0);
+        const int64_t zoff = (int64_t)rbase * args.ldz + (g_ok ? g : 0);
+        const float* zbase = (kBwd0 || ZST) ? nullptr : args.z_in + zoff;
+        const __half* zbase_h = (kBwd0 || ZST) ? nullptr : reinterpret_cast<const __half*>(args.z_in) + zoff;
         if constexpr (ZST) {
             if (!z_inflight) issue_z(cur.f0, rbase);
         }
@@ -969,14 +1002,29 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
                 for (int c = 0; c < KC; ++c) tmem_ld_n<TL>(taddr + cur.rb * (8 * KC) + c * 8 + i0, v[c]);
                 float zc[kBwd0 ? 1 : KC][TL];
                 if constexpr (ZST) {
-                    cp_async_wait_all();                               // (each lane reads back only what it copied itself)
+                    cp_async_wait_all();                               // (fp32: each lane reads back only what it copied itself)
                     float zf[KC * TL];
+                    if (args.z_half) {
+                        __syncwarp();                                  // the pair's other lane copied half of the entries
+                        static_for<KC * TL / 4>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            const uint4 t = lds_v4(z_addr + (lane >> 1) * kZLane + q * 16);
+                            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[e]);
+                                zf[4 * q + e] = (lane & 1) ? __high2float(h2) : __low2float(h2);
+                            }
+                        });
+                        __syncwarp();                                  // both lanes have read before the slot is refilled
+                    } else {
                     static_for<KC * TL / 4>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
                         const uint4 t = lds_v4(z_addr + lane * kZLane + q * 16);
                         zf[4 * q] = __uint_as_float(t.x); zf[4 * q + 1] = __uint_as_float(t.y);
                         zf[4 * q + 2] = __uint_as_float(t.z); zf[4 * q + 3] = __uint_as_float(t.w);
                     });
+                    }
 #pragma unroll
                     for (int c = 0; c < KC; ++c)
 #pragma unroll
@@ -994,7 +1042,8 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
 #pragma unroll
                         for (int j = 0; j < TL; ++j) {
                             const int rr = min(rbase + i0 + j, args.rows - 1) - rbase;
-                            zc[c][j] = g_ok ? __ldg(zbase + (int64_t)c * zplane + (int64_t)rr * args.ldz) : 0.f;
+                            const int64_t e = (int64_t)c * zplane + (int64_t)rr * args.ldz;
+                            zc[c][j] = !g_ok ? 0.f : args.z_half ? __half2float(__ldg(zbase_h + e)) : __ldg(zbase + e);
                         }
                 }
                 tmem_wait_ld();

@@ -287,6 +287,8 @@ const TcEnv& tc_env() {
         e.wgrad_tile_fastest = wo ? atoi(wo) : 1;
         const char* pk = getenv("STPDE_PACK");
         e.pack_narrow = pk ? atoi(pk) : 1;
+        const char* zh = getenv("STPDE_Z_HALF");
+        e.z_half = zh ? atoi(zh) : 1;
         const char* pdl = getenv("STPDE_PDL");
         e.pdl = pdl ? atoi(pdl) : 1;
         return e;

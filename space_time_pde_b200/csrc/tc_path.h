@@ -18,6 +18,7 @@ struct TcEnv {
     int l0_rows_per_warp;     // STPDE_L0_RPW: rows one warp of the layer-0 kernel walks (block = 8 warps x this many rows)
     int wgrad_tile_fastest;   // STPDE_WGRAD_ORDER=0: round-1 unit order of the weight-gradient kernel (slices of a tile adjacent)
     int pack_narrow;          // STPDE_PACK=0: narrow layers (<= 64 features) keep one row group per 128-lane tile
+    int z_half;               // STPDE_Z_HALF=0: the single-pass training mode keeps fp32 pre-activation planes
     int pdl;                  // STPDE_PDL=0: tensor-core kernels are launched without programmatic stream serialization
 };
 

@@ -409,6 +409,7 @@ def raw_backward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torc
             _setup_keys.pop(_slot(device), None)   # the shared workspace is about to be overwritten
         # The adjoints travel through fp16 hi/lo planes behind a power-of-two scale; if one overflows (status bit 1)
         # the sweep is repeated with 6 more bits of headroom.
+        desc.reserved[2] = 1 if (reuse and st.precision == "fp16") else 0   # the stash holds fp16 pre-activation planes
         for headroom in (0, 6, 12, 24):
             desc.reserved[0] = headroom
             status.zero_()

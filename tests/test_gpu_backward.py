@@ -280,6 +280,35 @@ def test_training_forward_stash_is_reused_and_invalidated(dev):
     assert tok2[0] != tok[0]
 
 
+def test_single_pass_stash_keeps_fp16_preactivations_consistent(dev):
+    """Single-pass training: the forward leaves fp16 pre-activation planes in the stash and tells the reverse sweep so
+    (desc.reserved[2]).  Every stash combination must give the gradients of its own recompute route: fp16 forward + fp16
+    sweep (fp16 planes), fp16x3 forward + fp16 sweep (fp32 planes read by a single-pass sweep), and a parity-mode sweep
+    must NOT reuse a single-pass stash."""
+    gen = torch.Generator().manual_seed(21)
+    d, c, o, nf, p = 3, 16, 4, 32, 1500
+    Ws, bs = make_decoder(gen, d, c, o, nf, dev)
+    grid = (torch.randn(1, 3, 4, 5, c, generator=gen) * 0.5).to(dev)
+    q = (torch.rand(1, p, d, generator=gen) * (1 - 2e-6) + 1e-6).to(dev)
+    spec = JetSpec(*RB2)
+    gy = torch.randn(1, p, o, generator=gen).to(dev)
+    gj = (torch.randn(spec.n_jet, 1, p, o, generator=gen) * 0.05).to(dev)
+    lo, hi = jets.bounds_tensors(0., 1., d, dev)
+    flat = lambda r: [r[0]] + r[1] + r[2]
+    ref16 = jets.raw_backward(grid, q, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16", gy, gj)          # recompute, fp16 planes
+    ref48 = jets.raw_backward(grid, q, lo, hi, Ws, bs, "softplus", 1.0, spec, "fp16x3", gy, gj)
+    for fwd_prec, bwd_prec, ref, tol in (("fp16", "fp16", ref16, 2e-6), ("fp16x3", "fp16", ref16, 5e-2),
+                                         ("fp16", "fp16x3", ref48, 2e-6)):
+        tok = []
+        jets.raw_forward(grid, q, lo, hi, Ws, bs, "softplus", 1.0, spec, fwd_prec, stash_out=tok)
+        got = jets.raw_backward(grid, q, lo, hi, Ws, bs, "softplus", 1.0, spec, bwd_prec, gy, gj, stash_token=tok[0])
+        for a, b in zip(flat(ref), flat(got)):
+            assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < tol, (fwd_prec, bwd_prec)
+    # and the single-pass gradients themselves stay inside the mode's gate against the parity-mode sweep
+    for a, b in zip(flat(ref48), flat(ref16)):
+        assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < BWD_TOLS["fp16"]
+
+
 def test_chunked_training_accumulates_like_one_batch(dev):
     """Walking the batch in chunks (each with its own stash) accumulates the same .grad as one big backward."""
     torch.manual_seed(2)

@@ -431,11 +431,11 @@ def test_deferred_checks_scope_and_late_report():
 def test_bench_plane_byte_accounting():
     """bench.plane_bytes_per_point: the HBM roofline of the nf = 32 legs counts every operand plane written once and read
     once (hand count for ImNet nf = 32, K = 6: 46 080 B per (point, corner) row in the parity mode; a training step in
-    the single-pass mode 79 104 B) and doubles with the hi + lo planes."""
+    the single-pass mode 66 816 B, its pre-activation planes being fp16 there) and doubles with the hi + lo planes."""
     import bench
     assert bench.imnet_widths(32) == [512, 256, 128, 64, 32]
     assert bench.plane_bytes_per_point(32, 3, 6, "fp16x3") == 8 * 46080
     assert bench.plane_bytes_per_point(32, 3, 6, "fp16") == 8 * 23040
-    assert bench.plane_bytes_per_point(32, 3, 6, "fp16", training=True) == 8 * 79104
+    assert bench.plane_bytes_per_point(32, 3, 6, "fp16", training=True) == 8 * 66816
     r = bench.hbm_roofline_of(1.0e7, 8 * 46080, {"hbm": 6551.0})
     assert r["bound"] == "hbm" and abs(r["frac"] - 1.0e7 * 8 * 46080 / 1e9 / 6551.0) < 1e-12
