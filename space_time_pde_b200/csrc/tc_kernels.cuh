@@ -1150,7 +1150,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const JetSpec& spec, const Lay
 #pragma unroll
                     for (int k = 0; k < kMaxDim; ++k) G[k] = fmaf(z0b, xr[k], G[k]);
                     // (exact zeros - padding rows, dead relu units - need no atomic)
-                    if (g_ok && r_ok && z0b != 0.f) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
+                    if (g_ok && r_ok && z0b != 0.f && args.g_vb) atomicAdd(args.g_vb + (int64_t)vrow * args.ncat + args.cat_off + g, z0b);
                 });
             });
             if constexpr (!kBwd0) {
