@@ -375,7 +375,6 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
     constexpr int SR = (OUTK == 1 && SRB < 8) ? 2 * SRB : SRB;     // one plane only: twice the rows fit the buffer
     constexpr int NBUF = kEpiBuffers;
     constexpr int NPASS = 8 / SR;
-    constexpr int kMyBlocks = (NRB - 1) / EPI_PQ + 1;              // upper bound of this warp's blocks per tile
     const bool has_blocks = sub < NRB;
     const float scale = __ldg(args.wscale);
     const int n_first = spec.n_first;
@@ -549,7 +548,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const JetSpec& spec, const Lay
         static_for<NPASS>([&](auto PS) {
             constexpr int ps = decltype(PS)::value;
             constexpr uint32_t kBufOff = NBUF > 1 ? (ps % NBUF) * (KC * SRB * 128) : 0;
-            const uint32_t sl = stg_addr + kBufOff + lane * (kF32 ? 4 : 2);
+            [[maybe_unused]] const uint32_t sl = stg_addr + kBufOff + lane * (kF32 ? 4 : 2);
             // TL rows at a time leave TMEM (a whole 8-row block in registers does not fit the 96-register budget next to
             // the prefetched skip terms: spilling those made the spill store wait for the very load it was hiding)
             constexpr int TL = SR < 4 ? SR : 4;
