@@ -112,7 +112,10 @@ typedef struct stpde_desc {
     int32_t precision;
     float xmin[STPDE_MAX_DIM];          /* float32 bounds exactly as the reference forms them */
     float xmax[STPDE_MAX_DIM];
-    int32_t reserved[8];                /* [2]: stpde_jet_backward with reuse_forward = 1: set to 1 when the forward that left
+    int32_t reserved[8];                /* [1]: stpde_jet_forward / stpde_jet_forward_train: 1 = the call-invariant setup in the
+                                           workspace (split weights, per-vertex table) was built by the previous call for exactly
+                                           these grid / weight values and is reused
+                                           [2]: stpde_jet_backward with reuse_forward = 1: set to 1 when the forward that left
                                            the planes ran with precision STPDE_PREC_FP16 (its pre-activation planes are fp16)
                                            [0]: backward only, extra headroom bits of the adjoint scale (0 = default)
                                          * [1]: stpde_jet_forward only, 1 = the call-invariant part of the workspace (packed /

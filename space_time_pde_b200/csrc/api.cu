@@ -415,7 +415,10 @@ static int run_backward(int mode, const Plan& P, const stpde_desc_t* d, const fl
     float* scale = (float*)(ws + P.off_bwd_scale + 256);
     const float* Wx[kMaxLayers] = {nullptr};
     prof_begin(kSlotSetup, st);
-    const bool prep = mode != kBwdReuse;     // kBwdReuse: the training forward left all of this in the workspace
+    // kBwdReuse: the training forward left all of this in the workspace; a training forward whose caller vouches
+    // (reserved[1] = 1) that the previous training forward in this workspace saw the same grid / weights skips it too -
+    // a step that walks its batch in chunks splits the weights and builds the vertex table once, not once per chunk
+    const bool prep = mode != kBwdReuse && !(mode == kBwdForwardOnly && d->reserved[1] == 1);
     for (int l = 0; l < P.n_layers; ++l) {
         float* wx = l < L ? (float*)(ws + P.off_wx[l]) : nullptr;
         Wx[l] = wx;

@@ -212,6 +212,7 @@ class _Stash:
         self.ws = ws
         self.token = 0
         self.precision = ""      # arithmetic of the forward that filled it (a single-pass forward leaves no lo planes)
+        self.setup_key = None    # (grid, weights, ...) whose call-invariant setup sits in the workspace's fixed region
 
 
 _stashes: Dict[tuple, _Stash] = {}
@@ -314,12 +315,22 @@ def raw_forward(grid: torch.Tensor, q: torch.Tensor, lo: torch.Tensor, hi: torch
             if nbytes and lib.stpde_backward_chunk_points(ctypes.byref(desc), nbytes) >= b * p:
                 st = _stash(device, nbytes)
                 st.token = 0
+                # chunks of one training step see the same grid / weights: the split weights and the per-vertex table of
+                # the previous training forward in this workspace are still valid (same tensors, same versions)
+                key = None
+                if os.environ.get("STPDE_SETUP_CACHE", "1") != "0":
+                    key = (st.ws.data_ptr(), grid.data_ptr(), grid._version, tuple(grid.shape), tuple(grid.stride()),
+                           tuple((w.data_ptr(), w._version) for w in list(Wc) + list(Bc)), tuple(widths), act,
+                           float(act_param), precision, tuple(float(v) for v in lo), tuple(float(v) for v in hi))
+                desc.reserved[1] = 1 if (key is not None and st.setup_key == key) else 0
+                st.setup_key = None
                 rc = lib.stpde_jet_forward_train(ctypes.byref(desc), grid.data_ptr(), gstr, q.data_ptr(), qstr, wptr,
                                                  bptr, y.data_ptr(), jets.data_ptr() if jets is not None else None,
                                                  st.ws.data_ptr(), st.ws.numel(), status.data_ptr(), stream)
                 _lib.check(rc)
                 st.token = next(_stash_tokens)
                 st.precision = precision
+                st.setup_key = key
                 stash_out.append(st.token)
                 subs = []
         for sub in subs:

@@ -309,6 +309,42 @@ def test_single_pass_stash_keeps_fp16_preactivations_consistent(dev):
         assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < BWD_TOLS["fp16"]
 
 
+def test_training_setup_cache_follows_weight_updates(dev, monkeypatch):
+    """Chunks of one training step reuse the split weights / per-vertex table of the previous training forward in the stash
+    (same tensors, same versions: desc.reserved[1]); an in-place optimizer update bumps the versions and the next forward
+    rebuilds them.  Gradients with the cache equal the gradients without it (STPDE_SETUP_CACHE=0)."""
+    torch.manual_seed(31)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=32, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = (torch.randn(2, 3, 4, 5, 16) * 0.5).to(dev).requires_grad_(True)
+    q = torch.rand(2, 1536, 3, device=dev) * (1 - 2e-6) + 1e-6
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+
+    def two_steps():
+        out = []
+        for _ in range(2):
+            opt.zero_grad(set_to_none=True)
+            grid.grad = None
+            for s0 in range(0, 1536, 512):                       # three chunks per step
+                y, sums, counts = layer.loss_sums(q[:, s0:s0 + 512], None, "l1")
+                (sums[0] / counts[0] + 0.0125 * sums[1] / counts[1]).backward()
+            out.append([grid.grad.clone()] + [p_.grad.clone() for p_ in model.parameters()])
+            opt.step()                                           # in-place: versions change, the cache must not survive
+        return out
+
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    with_cache = two_steps()
+    model.load_state_dict(state)
+    monkeypatch.setenv("STPDE_SETUP_CACHE", "0")
+    without = two_steps()
+    for step_a, step_b in zip(with_cache, without):
+        for a, b in zip(step_a, step_b):
+            assert rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 5e-6
+    # the second step really used the updated weights
+    assert rel_linf(with_cache[1][1].cpu().numpy(), with_cache[0][1].cpu().numpy()) > 1e-4
+
+
 def test_chunked_training_accumulates_like_one_batch(dev):
     """Walking the batch in chunks (each with its own stash) accumulates the same .grad as one big backward."""
     torch.manual_seed(2)
