@@ -325,6 +325,75 @@ def roofline_of(rate_per_gpu, fpt, peaks, passes, mult=1.0):
             "executed_frac": tf * passes / peaks["tflops"] if passes else None}
 
 
+def graphed_chunk_step(layer, params, q, target, chunk, loss_of_sums, device):
+    """One chunk of a training step (fused loss sums + reverse sweep, gradients ACCUMULATED into pre-existing .grad tensors)
+    recorded into CUDA graphs and replayed for every chunk of the batch: the ~85 launches of a chunk stop paying a launch
+    gap each (8 % of the BASELINE config-3 step).  Two graphs, because the call-invariant setup belongs to the FIRST chunk
+    after a weight update only: graph A rebuilds it (split weights, per-vertex table), graph B reuses it.  The library never
+    allocates, synchronises or reads device values on the host, so torch.cuda.graph can record the calls; their status words
+    stay on the device and are checked once per step.  Returns step() -> (reg_sum, pde_sum) or raises (the caller falls
+    back to the eager chunk loop)."""
+    from space_time_pde_b200 import jets
+    n = q.shape[1]
+    if n % chunk:
+        raise ValueError("graphed chunks need equal chunk sizes")
+    static_q = q[:, :chunk].clone()
+    static_t = target[:, :chunk].clone() if target is not None else None
+    reg_acc = torch.zeros((), device=device)
+    pde_acc = torch.zeros((), device=device)
+    for p_ in params:
+        p_.grad = torch.zeros_like(p_)                            # AccumulateGrad adds in place: the graphs accumulate
+
+    def body():
+        y, sums, _ = layer.loss_sums(static_q, static_t, "l1")
+        loss_of_sums(sums).backward()
+        reg_acc.add_(sums[0].detach())
+        pde_acc.add_(sums[1].detach())
+
+    old_cache = os.environ.get("STPDE_SETUP_CACHE")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    try:
+        os.environ["STPDE_SETUP_CACHE"] = "0"
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        g_first = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_first, stream=side):
+            body()
+        os.environ["STPDE_SETUP_CACHE"] = "1"
+        with torch.cuda.stream(side):
+            for _ in range(2):                                    # (the second call finds the first one's setup key)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        g_rest = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_rest, stream=side):
+            body()
+    finally:
+        if old_cache is None:
+            os.environ.pop("STPDE_SETUP_CACHE", None)
+        else:
+            os.environ["STPDE_SETUP_CACHE"] = old_cache
+    torch.cuda.synchronize()
+
+    def step():
+        for p_ in params:
+            p_.grad.zero_()
+        reg_acc.zero_()
+        pde_acc.zero_()
+        for i, s0 in enumerate(range(0, n, chunk)):
+            static_q.copy_(q[:, s0:s0 + chunk])
+            if static_t is not None:
+                static_t.copy_(target[:, s0:s0 + chunk])
+            (g_first if i == 0 else g_rest).replay()
+        jets.check_captured()                                     # status words of the captured calls (one sync per step)
+        return reg_acc, pde_acc
+
+    step.graphs = (g_first, g_rest)
+    return step
+
+
 # ----------------------------------------------------------------------------------------------
 # legs for the other BASELINE configurations
 # ----------------------------------------------------------------------------------------------
@@ -374,8 +443,34 @@ def leg_config2_train(ctx, args, model, grid, q, layer, peaks, lib):
         prof_t = _lib.profile_read()
         lib.stpde_profile_enable(0)
         means = out["means"]
+        eager_ms, graph_info = tms, None
+        if args.graph_chunks:
+            # the same step with each chunk replayed from a CUDA graph (same kernels, same losses; falls back to the loop)
+            eager_means = {k: float(v) for k, v in means.items()}
+            try:
+                denom = float(world * 4 * NPTS)
+                gstep = graphed_chunk_step(layer, params, q, None, tchunk,
+                                           lambda sums: sums[0] / denom + 0.0125 * sums[1] / denom, device)
+
+                def graph_step():
+                    reg_sum, pde_sum = gstep()
+                    out["means"] = reducer.reduce({"reg": reg_sum.clone(), "pde": pde_sum.clone()},
+                                                  {"reg": 4 * NPTS, "pde": 4 * NPTS})
+
+                graph_step()
+                gms = ctx.time(graph_step, args.train_steps, 0)
+                diff = max(abs(float(out["means"][k]) - eager_means[k]) / max(abs(eager_means[k]), 1e-30) for k in eager_means)
+                graph_info = {"ms_per_step": gms, "loss_rel_diff_vs_eager_loop": diff}
+                if diff < 1e-5 and gms < tms:
+                    tms = gms
+                del gstep
+                jets.check_captured(clear=True)
+            except Exception as exc:                              # noqa: BLE001 - optional path
+                graph_info = {"error": str(exc)[:200]}
+                jets._captured.clear()
         res = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
                "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
+               "eager_chunk_loop_ms_per_step": eager_ms, "cuda_graph_chunks": graph_info,
                "backward_precision": args.precision if args.train_backward_precision == "same" else args.train_backward_precision,
                "what": "config[1] training step: values + RB2 residuals + L1 losses + fused CUDA reverse sweep (grid + decoder "
                        "gradients), chunks of the batch with the forward planes kept for the backward (no recompute)"
@@ -449,6 +544,31 @@ def leg_config3(ctx, args, peaks):
         ms = ctx.time(step, 1, 0)
         prof = _lib.profile_read()
         lib.stpde_profile_enable(0)
+        eager_ms, graph_info = ms, None
+        if args.graph_chunks:
+            # the same step with each chunk replayed from a CUDA graph (same kernels, same losses; falls back to the loop)
+            eager_means = {k: float(v) for k, v in out["means"].items()}
+            try:
+                gstep = graphed_chunk_step(layer, params, q, target, chunk,
+                                           lambda sums: sums[0] / n_glob + 0.0125 * sums[1] / n_glob, device)
+
+                def graph_step():
+                    reg_sum, pde_sum = gstep()
+                    out["means"] = reducer.reduce({"reg": reg_sum.clone(), "pde": pde_sum.clone()},
+                                                  {"reg": n_glob / world, "pde": n_glob / world})
+
+                graph_step()
+                gms = ctx.time(graph_step, 1, 0)
+                diff = max(abs(float(out["means"][k]) - eager_means[k]) / max(abs(eager_means[k]), 1e-30) for k in eager_means)
+                graph_info = {"ms_per_step": gms, "loss_rel_diff_vs_eager_loop": diff}
+                if diff < 1e-5 and gms < ms:
+                    ms = gms
+                del gstep
+                jets.check_captured(clear=True)
+            except Exception as exc:                              # noqa: BLE001 - optional path
+                graph_info = {"error": str(exc)[:200]}
+                jets._captured.clear()
+                out["means"] = {k: torch.tensor(v) for k, v in eager_means.items()}
         with torch.no_grad():
             y, res = layer(q[:1, :512], return_residue=True)
         par = oracle_parity(model, grid, q, y, res, 256, rb2_kwargs=rb2)
@@ -459,6 +579,7 @@ def leg_config3(ctx, args, peaks):
                             "alpha_pde 0.0125, fused reverse sweep, one all-reduce of [loss sums | counts | gradients]",
                 "imnet_nf": nf, "jet_components": KC, "dtype": "f16 operands (single tcgen05 pass), f32 accumulate / jets / I/O",
                 "value": rate, "unit": "points/s (training step)", "ms_per_step": ms, "scaling": "strong (fixed 8 M points)",
+                "eager_chunk_loop_ms_per_step": eager_ms, "cuda_graph_chunks": graph_info,
                 "points_per_rank": B * p_rank, "chunk_points": B * chunk,
                 "roofline": roofline_of(rate / world, fpt, peaks, 1, mult=3.0),
                 "roofline_hbm": hbm_roofline_of(rate / world, plane_bytes_per_point(nf, 3, KC, "fp16", training=True), peaks),
@@ -755,6 +876,8 @@ def main():
     ap.add_argument("--legs", default="config2_train,config3,config4,config5,eval_grid",
                     help="comma-separated optional legs ('' = headline only)")
     ap.add_argument("--config3-chunk", type=int, default=65536, help="points (all crops) per chunk of the config-3 step")
+    ap.add_argument("--graph-chunks", type=int, default=1,
+                    help="1: the training legs also time their step with every chunk replayed from a CUDA graph (0: eager loop only)")
     ap.add_argument("--config4-points", type=int, default=1 << 20, help="query points per GPU of the config-4 leg (of 4 M)")
     ap.add_argument("--config5-points", type=lambda s: [int(float(x)) for x in s.split(",")], default=[10_000, 1_000_000, 64_000_000])
     ap.add_argument("--eval-grid", type=lambda s: tuple(int(x) for x in s.split("x")), default=(192, 128, 512))

@@ -53,6 +53,10 @@ class StepReducer:
         off = 2 * k
         for p in self.params:
             n = p.numel()
-            p.grad = flat[off:off + n].reshape(p.shape).to(p.dtype).clone()
+            g = flat[off:off + n].reshape(p.shape).to(p.dtype)
+            if p.grad is not None and p.grad.shape == g.shape and p.grad.dtype == g.dtype:
+                p.grad.copy_(g)          # in place: a step replayed from CUDA graphs accumulates into these very tensors
+            else:
+                p.grad = g.clone()
             off += n
         return means
