@@ -343,6 +343,7 @@ def graphed_chunk_step(layer, params, q, target, chunk, loss_of_sums, device):
     pde_acc = torch.zeros((), device=device)
     for p_ in params:
         p_.grad = torch.zeros_like(p_)                            # AccumulateGrad adds in place: the graphs accumulate
+    static_grads = [p_.grad for p_ in params]                     # ... into exactly these tensors
 
     def body():
         y, sums, _ = layer.loss_sums(static_q, static_t, "l1")
@@ -378,8 +379,9 @@ def graphed_chunk_step(layer, params, q, target, chunk, loss_of_sums, device):
     torch.cuda.synchronize()
 
     def step():
-        for p_ in params:
-            p_.grad.zero_()
+        for p_, g_ in zip(params, static_grads):
+            g_.zero_()
+            p_.grad = g_                                          # (whatever the caller did to .grad in between)
         reg_acc.zero_()
         pde_acc.zero_()
         for i, s0 in enumerate(range(0, n, chunk)):

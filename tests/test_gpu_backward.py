@@ -345,6 +345,55 @@ def test_training_setup_cache_follows_weight_updates(dev, monkeypatch):
     assert rel_linf(with_cache[1][1].cpu().numpy(), with_cache[0][1].cpu().numpy()) > 1e-4
 
 
+def test_chunks_replayed_from_cuda_graphs_accumulate_like_the_eager_loop(dev):
+    """bench.graphed_chunk_step: every chunk of a step replayed from a CUDA graph (graph A rebuilds the call-invariant
+    setup, graph B reuses it) accumulates the same gradients and loss sums as the eager chunk loop - also after an
+    in-place weight update between two steps (the first chunk's graph re-splits the weights)."""
+    import bench
+    torch.manual_seed(41)
+    model = sp.ImNet(dim=3, in_features=16, out_features=4, nf=32, activation=sp.NONLINEARITIES["softplus"]).to(dev)
+    grid = (torch.randn(2, 3, 4, 5, 16) * 0.5).to(dev).requires_grad_(True)
+    q = torch.rand(2, 1536, 3, device=dev) * (1 - 2e-6) + 1e-6
+    target = torch.randn(2, 1536, 4, device=dev)
+    layer = sp.get_rb2_pde_layer(t_crop=2., z_crop=1., x_crop=1., use_continuity=True)
+    layer.update_forward_method(lambda pts: sp.query_local_implicit_grid(model, grid, pts, 0., 1.))
+    params = [grid] + list(model.parameters())
+    loss_of = lambda sums: sums[0] * 1e-3 + 0.0125 * sums[1] * 1e-3
+
+    def eager():
+        for p_ in params:
+            p_.grad = None
+        tot = torch.zeros(2, device=dev)
+        for s0 in range(0, 1536, 512):
+            y, sums, _ = layer.loss_sums(q[:, s0:s0 + 512], target[:, s0:s0 + 512], "l1")
+            loss_of(sums).backward()
+            tot += torch.stack([sums[0].detach(), sums[1].detach()])
+        return tot, [p_.grad.clone() for p_ in params]
+
+    for round_ in range(2):
+        tot_e, g_e = eager()
+        gstep = bench.graphed_chunk_step(layer, params, q, target, 512, loss_of, dev)
+        for _ in range(2):                                       # replaying twice gives the same step twice
+            reg, pde = gstep()
+            assert rel_linf(torch.stack([reg, pde]).cpu().numpy(), tot_e.cpu().numpy()) < 1e-6
+            for a, b in zip(g_e, [p_.grad for p_ in params]):
+                assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < 5e-6
+        if round_ == 0:
+            # in-place update (as an optimizer does): the captured graphs read the weights through the same pointers
+            with torch.no_grad():
+                for p_ in model.parameters():
+                    p_.add_(0.01 * torch.randn_like(p_))
+            tot_u, g_u = eager()
+            reg, pde = gstep()
+            assert rel_linf(torch.stack([reg, pde]).cpu().numpy(), tot_u.cpu().numpy()) < 1e-6
+            for a, b in zip(g_u, [p_.grad for p_ in params]):
+                assert rel_linf(b.cpu().numpy(), a.cpu().numpy()) < 5e-6
+        del gstep
+        jets.check_captured(clear=True)
+    for p_ in params:
+        p_.grad = None
+
+
 def test_chunked_training_accumulates_like_one_batch(dev):
     """Walking the batch in chunks (each with its own stash) accumulates the same .grad as one big backward."""
     torch.manual_seed(2)
