@@ -235,6 +235,16 @@ class Ctx:
             return float(t.item())
         return float(ms)
 
+    def all_ok(self, ok):
+        """True only if `ok` holds on EVERY rank (an optional path must be taken or skipped by all ranks alike: its timing
+        runs barriers and an all-reduce)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([1.0 if ok else 0.0], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item() > 0.5)
+        return bool(ok)
+
     def time(self, fn, steps, warmup):
         """ms per step: CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
         for _ in range(warmup):
@@ -449,10 +459,15 @@ def leg_config2_train(ctx, args, model, grid, q, layer, peaks, lib):
         if args.graph_chunks:
             # the same step with each chunk replayed from a CUDA graph (same kernels, same losses; falls back to the loop)
             eager_means = {k: float(v) for k, v in means.items()}
-            try:
-                denom = float(world * 4 * NPTS)
+            denom = float(world * 4 * NPTS)
+            gstep = None
+            try:                                                  # phase 1 (local): record the graphs
                 gstep = graphed_chunk_step(layer, params, q, None, tchunk,
                                            lambda sums: sums[0] / denom + 0.0125 * sums[1] / denom, device)
+            except Exception as exc:                              # noqa: BLE001 - optional path
+                graph_info = {"error": str(exc)[:200]}
+                jets._captured.clear()
+            if ctx.all_ok(gstep is not None):                     # phase 2 (collective): every rank or none
 
                 def graph_step():
                     reg_sum, pde_sum = gstep()
@@ -465,11 +480,10 @@ def leg_config2_train(ctx, args, model, grid, q, layer, peaks, lib):
                 graph_info = {"ms_per_step": gms, "loss_rel_diff_vs_eager_loop": diff}
                 if diff < 1e-5 and gms < tms:
                     tms = gms
-                del gstep
-                jets.check_captured(clear=True)
-            except Exception as exc:                              # noqa: BLE001 - optional path
-                graph_info = {"error": str(exc)[:200]}
-                jets._captured.clear()
+            elif graph_info is None:
+                graph_info = {"error": "graph capture failed on another rank"}
+            gstep = None
+            jets._captured.clear()
         res = {"value": world * NPTS / (tms * 1e-3), "unit": "points/s", "ms_per_step": tms, "steps": args.train_steps,
                "chunk_points": tchunk, "workspace_mb": args.train_workspace_mb,
                "eager_chunk_loop_ms_per_step": eager_ms, "cuda_graph_chunks": graph_info,
@@ -550,9 +564,14 @@ def leg_config3(ctx, args, peaks):
         if args.graph_chunks:
             # the same step with each chunk replayed from a CUDA graph (same kernels, same losses; falls back to the loop)
             eager_means = {k: float(v) for k, v in out["means"].items()}
-            try:
+            gstep = None
+            try:                                                  # phase 1 (local): record the graphs
                 gstep = graphed_chunk_step(layer, params, q, target, chunk,
                                            lambda sums: sums[0] / n_glob + 0.0125 * sums[1] / n_glob, device)
+            except Exception as exc:                              # noqa: BLE001 - optional path
+                graph_info = {"error": str(exc)[:200]}
+                jets._captured.clear()
+            if ctx.all_ok(gstep is not None):                     # phase 2 (collective): every rank or none
 
                 def graph_step():
                     reg_sum, pde_sum = gstep()
@@ -565,12 +584,11 @@ def leg_config3(ctx, args, peaks):
                 graph_info = {"ms_per_step": gms, "loss_rel_diff_vs_eager_loop": diff}
                 if diff < 1e-5 and gms < ms:
                     ms = gms
-                del gstep
-                jets.check_captured(clear=True)
-            except Exception as exc:                              # noqa: BLE001 - optional path
-                graph_info = {"error": str(exc)[:200]}
-                jets._captured.clear()
-                out["means"] = {k: torch.tensor(v) for k, v in eager_means.items()}
+            elif graph_info is None:
+                graph_info = {"error": "graph capture failed on another rank"}
+            gstep = None
+            jets._captured.clear()
+            out["means"] = {k: torch.tensor(v) for k, v in eager_means.items()}
         with torch.no_grad():
             y, res = layer(q[:1, :512], return_residue=True)
         par = oracle_parity(model, grid, q, y, res, 256, rb2_kwargs=rb2)
