@@ -111,3 +111,36 @@ def test_ddp_wrapped_decoder_gradients_are_averaged_across_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert across == 0.0 and err < 1e-6
+
+
+def _all_ok_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    ctx = bench.Ctx(torch.device("cpu"), rank, world)
+    # an optional path (CUDA-graph replay of the training chunks) is taken by every rank or by none
+    res = (ctx.all_ok(True), ctx.all_ok(rank != 1), ctx.all_ok(False))
+    # the reducer writes the reduced gradients INTO pre-existing .grad tensors (graph replays accumulate into them)
+    w = torch.nn.Parameter(torch.ones(3))
+    w.grad = torch.full((3,), float(rank + 1))
+    keep = w.grad
+    StepReducer([w]).reduce({"reg": torch.tensor(1.0)}, {"reg": 1.0})
+    out.put((rank, res, keep is w.grad, w.grad.tolist()))
+    dist.destroy_process_group()
+
+
+def test_optional_paths_are_taken_by_all_ranks_or_none_and_grads_stay_in_place():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_all_ok_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, same_tensor, grad in got:
+        assert res == (True, False, False)
+        assert same_tensor and grad == [3.0, 3.0, 3.0]          # 1 + 2 summed over the ranks, written in place
